@@ -1,0 +1,216 @@
+"""ctypes front-end for the TEST-ONLY checkers under oracle/.
+
+* ``Oracle``  -> oracle/liboracle.so   (our C restatement, oracle/fpng_oracle.c; always buildable)
+* ``Ref``     -> oracle/_ref/libfpng_ref.so (the unmodified reference + lodepng + stb_image, built from
+                 /root/reference/src by oracle/Makefile when that tree exists; travels prebuilt to the GPU box)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+The product package (fpng_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libfpng_ref.so")
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (and _ref/libfpng_ref.so when the reference sources are present)."""
+    src = os.path.join(HERE, "fpng_oracle.c")
+    stale = (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src)
+    ref_possible = os.path.exists("/root/reference/src/fpng.cpp")
+    ref_stale = ref_possible and (
+        (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_shim.cpp")))
+    if force or stale or ref_stale:
+        subprocess.check_call(["make", "-s", "-f", os.path.join(HERE, "Makefile"), "all"], cwd=HERE)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _as_u8(buf) -> np.ndarray:
+    if isinstance(buf, np.ndarray):
+        return np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+    return np.frombuffer(bytes(buf), dtype=np.uint8)
+
+
+class Oracle:
+    def __init__(self):
+        build()
+        L = C.CDLL(ORACLE_SO)
+        L.oracle_init.restype = None
+        L.oracle_crc32.restype = C.c_uint32
+        L.oracle_crc32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+        L.oracle_adler32.restype = C.c_uint32
+        L.oracle_adler32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+        L.oracle_max_encoded_size.restype = C.c_size_t
+        L.oracle_max_encoded_size.argtypes = [C.c_uint32] * 3
+        L.oracle_encode_ex.restype = C.c_size_t
+        L.oracle_encode_ex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                       C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
+        L.oracle_decode.restype = C.c_int
+        L.oracle_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, u32p, u32p, u32p, C.c_uint32]
+        L.oracle_get_info.restype = C.c_int
+        L.oracle_get_info.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, u32p]
+        L.oracle_static_table.restype = None
+        L.oracle_static_table.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, u32p]
+        L.oracle_init()
+        self.L = L
+
+    def crc32(self, data, prev=0) -> int:
+        a = _as_u8(data)
+        return self.L.oracle_crc32(_ptr(a), a.size, prev)
+
+    def adler32(self, data, prev=1) -> int:
+        a = _as_u8(data)
+        return self.L.oracle_adler32(_ptr(a), a.size, prev)
+
+    def max_encoded_size(self, w, h, chans) -> int:
+        return self.L.oracle_max_encoded_size(w, h, chans)
+
+    def encode(self, img, w, h, chans, flags=0, want_rows=False):
+        a = _as_u8(img)
+        assert a.size == w * h * chans
+        cap = self.max_encoded_size(w, h, chans)
+        out = np.empty(cap, dtype=np.uint8)
+        rows = np.zeros(h, dtype=np.uint64) if want_rows else None
+        stored = C.c_int(0)
+        n = self.L.oracle_encode_ex(_ptr(a), w, h, chans, flags, _ptr(out), cap,
+                                    _ptr(rows) if want_rows else None, C.byref(stored))
+        if n == 0:
+            raise ValueError("oracle_encode rejected the arguments")
+        data = out[:n].tobytes()
+        if want_rows:
+            return data, rows, bool(stored.value)
+        return data
+
+    def static_table(self, chans):
+        sizes = np.zeros(288, np.uint8)
+        codes = np.zeros(288, np.uint16)
+        hb = C.c_uint32(0)
+        self.L.oracle_static_table(chans, _ptr(sizes), _ptr(codes), C.byref(hb))
+        return sizes, codes, hb.value
+
+    def get_info(self, data):
+        a = _as_u8(data)
+        w, h, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        st = self.L.oracle_get_info(_ptr(a), a.size, C.byref(w), C.byref(h), C.byref(c))
+        return st, w.value, h.value, c.value
+
+    def decode(self, data, desired):
+        a = _as_u8(data)
+        st, w, h, c = self.get_info(a)
+        cap = max(1, w * h * max(desired, 1)) if st == 0 and desired in (3, 4) else 1
+        out = np.empty(cap, dtype=np.uint8)
+        ww, hh, cc = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        st = self.L.oracle_decode(_ptr(a), a.size, _ptr(out), cap, C.byref(ww), C.byref(hh), C.byref(cc), desired)
+        px = out[: ww.value * hh.value * desired].copy() if st == 0 else None
+        return st, px, ww.value, hh.value, cc.value
+
+
+class Ref:
+    """The compiled, unmodified reference (fpng v1.0.6) plus lodepng and stb_image verifiers."""
+
+    @staticmethod
+    def available() -> bool:
+        try:
+            build()
+        except Exception:
+            pass
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        if not Ref.available():
+            raise RuntimeError("oracle/_ref/libfpng_ref.so is not built (reference sources absent?)")
+        L = C.CDLL(REF_SO)
+        L.ref_init.restype = None
+        L.ref_cpu_supports_sse41.restype = C.c_int
+        L.ref_crc32.restype = C.c_uint32
+        L.ref_crc32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+        L.ref_adler32.restype = C.c_uint32
+        L.ref_adler32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+        L.ref_encode.restype = C.c_size_t
+        L.ref_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
+        L.ref_encode_discard.restype = C.c_size_t
+        L.ref_encode_discard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.ref_get_info.restype = C.c_int
+        L.ref_get_info.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, u32p]
+        L.ref_decode.restype = C.c_int
+        L.ref_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, u32p, u32p, u32p, C.c_uint32]
+        L.ref_lodepng_decode.restype = C.c_uint
+        L.ref_lodepng_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, u32p, u32p, C.c_uint32]
+        L.ref_stb_decode.restype = C.c_int
+        L.ref_stb_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, u32p, u32p, C.c_int]
+        L.ref_init()
+        self.L = L
+
+    def sse41(self) -> bool:
+        return bool(self.L.ref_cpu_supports_sse41())
+
+    def crc32(self, data, prev=0):
+        a = _as_u8(data)
+        return self.L.ref_crc32(_ptr(a), a.size, prev)
+
+    def adler32(self, data, prev=1):
+        a = _as_u8(data)
+        return self.L.ref_adler32(_ptr(a), a.size, prev)
+
+    def encode(self, img, w, h, chans, flags=0) -> bytes:
+        a = _as_u8(img)
+        assert a.size == w * h * chans
+        cap = 58 + 6 + (w * chans + 1) * h + 5 * (((w * chans + 1) * h + 65534) // 65535) + 16 + 64
+        out = np.empty(cap, dtype=np.uint8)
+        n = self.L.ref_encode(_ptr(a), w, h, chans, flags, _ptr(out), cap)
+        if n == 0 or n > cap:
+            raise ValueError("reference encoder failed")
+        return out[:n].tobytes()
+
+    def encode_discard(self, img, w, h, chans, flags=0, reps=1) -> int:
+        a = _as_u8(img)
+        return self.L.ref_encode_discard(_ptr(a), w, h, chans, flags, reps)
+
+    def get_info(self, data):
+        a = _as_u8(data)
+        w, h, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        st = self.L.ref_get_info(_ptr(a), a.size, C.byref(w), C.byref(h), C.byref(c))
+        return st, w.value, h.value, c.value
+
+    def decode(self, data, desired):
+        a = _as_u8(data)
+        st, w, h, c = self.get_info(a)
+        cap = max(1, w * h * 4)
+        out = np.empty(cap, dtype=np.uint8)
+        ww, hh, cc = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        st = self.L.ref_decode(_ptr(a), a.size, _ptr(out), cap, C.byref(ww), C.byref(hh), C.byref(cc), desired)
+        px = out[: ww.value * hh.value * desired].copy() if st == 0 else None
+        return st, px, ww.value, hh.value, cc.value
+
+    def lodepng_decode(self, data, want_chans):
+        a = _as_u8(data)
+        st, w, h, c = self.get_info(a)
+        if w == 0 or h == 0:   # not parsable by fpng's walker: let lodepng find dimensions with a big buffer
+            w, h = 8192, 8192
+        out = np.empty(w * h * want_chans, dtype=np.uint8)
+        ww, hh = C.c_uint32(), C.c_uint32()
+        err = self.L.ref_lodepng_decode(_ptr(a), a.size, _ptr(out), out.size, C.byref(ww), C.byref(hh), want_chans)
+        px = out[: ww.value * hh.value * want_chans].copy() if err == 0 else None
+        return err, px, ww.value, hh.value
+
+    def stb_decode(self, data, want_chans):
+        a = _as_u8(data)
+        st, w, h, c = self.get_info(a)
+        out = np.empty(max(1, w * h * want_chans), dtype=np.uint8)
+        ww, hh = C.c_uint32(), C.c_uint32()
+        comp = self.L.ref_stb_decode(_ptr(a), a.size, _ptr(out), out.size, C.byref(ww), C.byref(hh), want_chans)
+        px = out[: ww.value * hh.value * want_chans].copy() if comp else None
+        return comp, px, ww.value, hh.value
