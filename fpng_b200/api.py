@@ -1,0 +1,149 @@
+"""Python mirror of the reference's operator interface (src/fpng.h:13-111) over the C ABI.
+
+Reference signature                                        -> here
+  fpng_init()                                              -> fpng_init(device=-1)
+  fpng_encode_image_to_memory(pImage,w,h,chans,out,flags)  -> fpng_encode_image_to_memory(image,w,h,chans,flags) -> (ok, bytes)
+  fpng_decode_memory(pImage,size,out,w,h,chans,desired)    -> fpng_decode_memory(data, desired) -> (status, pixels, w, h, chans)
+Errors follow the reference: encode returns (False, b"") on invalid arguments, decode returns the FPNG_DECODE_* codes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import FpngB200Error, check, lib
+
+FPNG_ENCODE_SLOWER = 1          # src/fpng.h:38
+FPNG_FORCE_UNCOMPRESSED = 2     # src/fpng.h:41
+(FPNG_DECODE_SUCCESS, FPNG_DECODE_NOT_FPNG, FPNG_DECODE_INVALID_ARG, FPNG_DECODE_FAILED_NOT_PNG,
+ FPNG_DECODE_FAILED_HEADER_CRC32, FPNG_DECODE_FAILED_INVALID_DIMENSIONS, FPNG_DECODE_FAILED_DIMENSIONS_TOO_LARGE,
+ FPNG_DECODE_FAILED_CHUNK_PARSING, FPNG_DECODE_FAILED_INVALID_IDAT, FPNG_DECODE_FILE_OPEN_FAILED,
+ FPNG_DECODE_FILE_TOO_LARGE, FPNG_DECODE_FILE_READ_FAILED, FPNG_DECODE_FILE_SEEK_FAILED) = range(13)   # src/fpng.h:57-77
+
+
+def _u8(buf) -> np.ndarray:
+    if isinstance(buf, np.ndarray):
+        return np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+    return np.frombuffer(bytes(buf), dtype=np.uint8)
+
+
+def fpng_init(device: int = -1) -> None:
+    """src/fpng.h:17. Brings up the CUDA side (device, stream, code books). Raises when no GPU is present."""
+    check(lib().fpngb_init(device), "fpng_init")
+
+
+def fpng_cpu_supports_sse41() -> bool:
+    """src/fpng.h:23. Kept for API completeness; this implementation has no CPU SIMD path, so always False."""
+    if not lib().fpngb_is_initialized():
+        raise FpngB200Error("fpng_cpu_supports_sse41: fpng_init() must be called first")
+    return False
+
+
+def launch_count() -> int:
+    return int(lib().fpngb_launch_count())
+
+
+def max_encoded_size(w: int, h: int, chans: int) -> int:
+    return int(lib().fpngb_max_encoded_size(w, h, chans))
+
+
+def fpng_crc32(data, prev_crc32: int = 0) -> int:
+    a = _u8(data)
+    return int(lib().fpngb_crc32(a.ctypes.data_as(C.c_void_p), a.size, prev_crc32))
+
+
+def fpng_adler32(data, adler: int = 1) -> int:
+    a = _u8(data)
+    return int(lib().fpngb_adler32(a.ctypes.data_as(C.c_void_p), a.size, adler))
+
+
+def fpng_encode_image_to_memory(image, w: int, h: int, num_chans: int, flags: int = 0):
+    """src/fpng.h:48 / src/fpng.cpp:1662.  Returns (ok, png_bytes)."""
+    L = lib()
+    if w < 1 or h < 1 or num_chans not in (3, 4) or w > (1 << 24) or h > (1 << 24) or w * h > 0xFFFFFFFF:
+        return False, b""
+    a = _u8(image)
+    if a.size != w * h * num_chans:
+        return False, b""
+    cap = max_encoded_size(w, h, num_chans)
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t(0)
+    rc = L.fpngb_encode_host(a.ctypes.data_as(C.c_void_p), w, h, num_chans, flags, out.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+    if rc == 1:
+        return False, b""
+    check(rc, "fpng_encode_image_to_memory")
+    return True, out[: n.value].tobytes()
+
+
+def fpng_encode_image_to_file(filename: str, image, w: int, h: int, num_chans: int, flags: int = 0) -> bool:
+    """src/fpng.h:52."""
+    ok, data = fpng_encode_image_to_memory(image, w, h, num_chans, flags)
+    if not ok:
+        return False
+    try:
+        with open(filename, "wb") as f:
+            f.write(data)
+    except OSError:
+        return False
+    return True
+
+
+def fpng_get_info(data):
+    """src/fpng.h:92. Returns (status, w, h, channels_in_file)."""
+    a = _u8(data)
+    w, h, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    st = lib().fpngb_get_info(a.ctypes.data_as(C.c_void_p), a.size, C.byref(w), C.byref(h), C.byref(c))
+    return st, w.value, h.value, c.value
+
+
+def fpng_decode_memory(data, desired_channels: int):
+    """src/fpng.h:108. Returns (status, pixels|None, w, h, channels_in_file)."""
+    a = _u8(data)
+    if a.size == 0 or desired_channels not in (3, 4):
+        return FPNG_DECODE_INVALID_ARG, None, 0, 0, 0
+    st, w, h, c = fpng_get_info(a)
+    if st != FPNG_DECODE_SUCCESS:
+        return st, None, w, h, c
+    need = w * h * desired_channels
+    if need > 0xFFFFFFFF:
+        return FPNG_DECODE_FAILED_DIMENSIONS_TOO_LARGE, None, w, h, c
+    out = np.empty(need, dtype=np.uint8)
+    ww, hh, cc = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    st = lib().fpngb_decode_host(a.ctypes.data_as(C.c_void_p), a.size, out.ctypes.data_as(C.c_void_p), need,
+                                 C.byref(ww), C.byref(hh), C.byref(cc), desired_channels)
+    return st, (out if st == 0 else None), ww.value, hh.value, cc.value
+
+
+def fpng_decode_file(filename: str, desired_channels: int):
+    """src/fpng.h:111."""
+    try:
+        with open(filename, "rb") as f:
+            data = f.read()
+    except OSError:
+        return FPNG_DECODE_FILE_OPEN_FAILED, None, 0, 0, 0
+    if len(data) > 0xFFFFFFFF:
+        return FPNG_DECODE_FILE_TOO_LARGE, None, 0, 0, 0
+    return fpng_decode_memory(data, desired_channels)
+
+
+def encode_batch_device(images, flags: int = 0, out=None, sizes=None, stream=None):
+    """Encode a batch of equally sized device-resident images.
+
+    images: torch.uint8 CUDA tensor [n, h, w, chans] (contiguous). Returns (out [n, stride] uint8, sizes [n] int32 holding
+    uint32 file sizes) on the same device; kernels are enqueued on the current torch stream (or `stream`), not synchronised.
+    """
+    import torch
+
+    assert images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous() and images.dim() == 4
+    n, h, w, c = images.shape
+    stride = (max_encoded_size(w, h, c) + 15) // 16 * 16
+    if out is None:
+        out = torch.empty((n, stride), dtype=torch.uint8, device=images.device)
+    if sizes is None:
+        sizes = torch.empty((n,), dtype=torch.int32, device=images.device)
+    s = stream if stream is not None else torch.cuda.current_stream(images.device).cuda_stream
+    rc = lib().fpngb_encode_batch_device(images.data_ptr(), h * w * c, n, w, h, c, flags, out.data_ptr(), out.stride(0),
+                                         sizes.data_ptr(), s)
+    check(rc, "encode_batch_device")
+    return out, sizes

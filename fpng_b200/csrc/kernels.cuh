@@ -1,0 +1,75 @@
+// fpng_b200/csrc/kernels.cuh -- kernel parameter blocks and launcher prototypes (host_api.cu <-> *_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace fpngb {
+
+constexpr int kRowsPerBlock = 8;                  // one warp per scanline, 8 scanlines per CTA
+constexpr int kScanThreads = 32 * kRowsPerBlock;
+constexpr int kPackThreads = 32 * kRowsPerBlock;
+constexpr int kOffsetsThreads = 256;
+constexpr int kStageWords = 272;                  // >= (31 + 12 + 128 * 66) / 32 + 1 words per 128-pixel step
+
+struct ScanParams {
+    const uint8_t* pixels; size_t image_stride;   // n images, tightly packed rows (pitch = w * chans)
+    uint32_t w, h;
+    const CodeBook* books; uint32_t book_stride;  // 0: one shared (1-pass) book, 1: per-image books (2-pass)
+    uint32_t* row_bits;                           // [n*h] token bits per row (incl. the filter literal)
+    uint2* row_adler;                             // [n*h] (S1, S2) mod 65521 of the filtered row
+    ImageState* st;                               // [n]
+    uint32_t* hist;                               // [n*288] (histogram mode)
+    uint32_t merge_first_unit;                    // RGB 1-pass: filter literal and pixel 0 share a flush unit (fpng.cpp:1187-1203)
+};
+
+struct OffsetsParams {
+    const uint32_t* row_bits; unsigned long long* row_ofs;
+    const CodeBook* books; uint32_t book_stride;
+    ImageState* st;
+    uint8_t* out; size_t out_stride; uint32_t* sizes;
+    uint32_t w, h, chans, flags;
+    uint8_t png_header[kPngHeaderSize];           // IDAT length patched per image on device
+};
+
+struct PackParams {
+    const uint8_t* pixels; size_t image_stride;
+    uint32_t w, h;
+    const CodeBook* books; uint32_t book_stride;
+    const unsigned long long* row_ofs;
+    uint2* row_adler;                             // rewritten for stored images (raw bytes, filter 0)
+    const ImageState* st;
+    uint8_t* out; size_t out_stride;
+};
+
+struct AdlerParams {
+    const uint2* row_adler; ImageState* st;
+    uint8_t* out; size_t out_stride;
+    uint32_t w, h, chans;
+};
+
+struct CrcParams {
+    uint8_t* out; size_t out_stride;
+    ImageState* st;
+    uint32_t max_tiles;                           // grid.x; CTAs beyond an image's length exit immediately
+    uint32_t msg_start;                           // first byte of the CRC'd region (54 = "IDAT" for a PNG file)
+    uint32_t init_xor;                            // initial register value (0xFFFFFFFF for a fresh CRC)
+};
+
+struct HuffParams {
+    const uint32_t* hist;                         // [n*288]
+    CodeBook* books;                              // [n]
+    uint32_t chans;
+};
+
+void launch_scan(const ScanParams& p, uint32_t n, uint32_t chans, int mode, bool hist, cudaStream_t s);
+void launch_offsets(const OffsetsParams& p, uint32_t n, cudaStream_t s);
+void launch_pack(const PackParams& p, uint32_t n, uint32_t chans, int mode, cudaStream_t s);
+void launch_adler_finalize(const AdlerParams& p, uint32_t n, cudaStream_t s);
+void launch_crc(const CrcParams& p, uint32_t n, cudaStream_t s);
+void launch_huffman_build(const HuffParams& p, uint32_t n, cudaStream_t s);
+uint32_t crc_ctas_for(size_t max_file_bytes);
+int  checksum_tables_init();                      // uploads CRC slice tables / x^(2^k) powers (idempotent)
+
+// host helpers shared by host_api.cu and the tests
+uint32_t host_crc32(const void* data, size_t n, uint32_t prev);
+
+}  // namespace fpngb

@@ -1,0 +1,111 @@
+/*
+ * include/fpng_b200.h -- C ABI of the B200-native fpng hot path (libfpng_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  The C++ wrappers in
+ * include/fpng.h (namespace fpng, same signatures as the reference's src/fpng.h:13-111) and the Python
+ * package fpng_b200 are thin layers over these entry points.  Every function cites the reference interface it
+ * replaces.  All functions return 0 (FPNGB_OK) on success unless stated otherwise; nothing throws.
+ *
+ * Error codes: 1..99 = argument/usage errors below; fpngb_decode_* return the reference's FPNG_DECODE_* values
+ * (src/fpng.h:57-77) unchanged; 1000 + cudaError_t for CUDA runtime failures.
+ */
+#ifndef FPNG_B200_H
+#define FPNG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPNGB_API __attribute__((visibility("default")))
+
+enum {
+    FPNGB_OK = 0,
+    FPNGB_ERR_INVALID_ARG = 1,       /* reference: fpng_encode_image_to_memory returns false (src/fpng.cpp:1670-1680) */
+    FPNGB_ERR_BUFFER_TOO_SMALL = 2,
+    FPNGB_ERR_NOT_INITIALIZED = 3,
+    FPNGB_ERR_NO_DEVICE = 4,         /* no CUDA device: there is deliberately NO CPU fallback */
+    FPNGB_ERR_ALIGNMENT = 5,
+    FPNGB_ERR_INTERNAL = 6
+};
+
+/* encode flags, bit-compatible with src/fpng.h:34-42 */
+enum { FPNGB_ENCODE_SLOWER = 1, FPNGB_FORCE_UNCOMPRESSED = 2 };
+
+/* decode status, value-compatible with src/fpng.h:57-77 */
+enum {
+    FPNGB_DECODE_SUCCESS = 0, FPNGB_DECODE_NOT_FPNG, FPNGB_DECODE_INVALID_ARG, FPNGB_DECODE_FAILED_NOT_PNG,
+    FPNGB_DECODE_FAILED_HEADER_CRC32, FPNGB_DECODE_FAILED_INVALID_DIMENSIONS,
+    FPNGB_DECODE_FAILED_DIMENSIONS_TOO_LARGE, FPNGB_DECODE_FAILED_CHUNK_PARSING, FPNGB_DECODE_FAILED_INVALID_IDAT,
+    FPNGB_DECODE_FILE_OPEN_FAILED, FPNGB_DECODE_FILE_TOO_LARGE, FPNGB_DECODE_FILE_READ_FAILED,
+    FPNGB_DECODE_FILE_SEEK_FAILED
+};
+
+/* Replaces fpng::fpng_init() (src/fpng.h:17, src/fpng.cpp:373-376: CPU feature detection).  Here: selects the CUDA
+ * device (-1 = current), creates the stream, uploads the static Huffman code books / checksum tables.  Idempotent,
+ * thread-safe.  Fails with FPNGB_ERR_NO_DEVICE when no GPU is present. */
+FPNGB_API int fpngb_init(int device);
+FPNGB_API int fpngb_is_initialized(void);
+FPNGB_API const char* fpngb_version(void);
+
+/* Upper bound of the encoded file size for a w x h x chans image: max of the stored-block layout
+ * (src/fpng.cpp:1747) and the compressed-path working buffer (src/fpng.cpp:1705), plus header and trailer. */
+FPNGB_API size_t fpngb_max_encoded_size(uint32_t w, uint32_t h, uint32_t chans);
+
+/* Replaces fpng::fpng_encode_image_to_memory (src/fpng.h:48, src/fpng.cpp:1662-1803) for HOST buffers:
+ * pixels (tightly packed, pitch w*chans, R first) -> PNG file bytes in out[0..*out_size).  out_cap must be at least
+ * fpngb_max_encoded_size().  Copies host->device, runs the CUDA kernels, copies the file back; returns after the
+ * result is in host memory.  Output is byte-identical to the reference encoder for the same flags. */
+FPNGB_API int fpngb_encode_host(const void* pixels, uint32_t w, uint32_t h, uint32_t chans, uint32_t flags,
+                                void* out, size_t out_cap, size_t* out_size);
+
+/* Batch of n equally sized images resident in DEVICE memory -> n PNG files in device memory.
+ *   d_pixels + i*image_stride : image i (tightly packed rows)
+ *   d_out    + i*out_stride   : file i; out_stride >= fpngb_max_encoded_size(), multiple of 16; d_out 16-byte aligned
+ *   d_sizes[i]                : file size in bytes (device memory, n x uint32)
+ * All kernels are enqueued on `stream` (a cudaStream_t; NULL = the library's own stream); the call does not
+ * synchronise.  This is the path bench.py times; it is what one rank runs on its shard of a multi-GPU batch. */
+FPNGB_API int fpngb_encode_batch_device(const void* d_pixels, size_t image_stride, uint32_t n,
+                                        uint32_t w, uint32_t h, uint32_t chans, uint32_t flags,
+                                        void* d_out, size_t out_stride, uint32_t* d_sizes, void* stream);
+
+/* Batch of n equally sized images in HOST memory (ideally pinned: see fpngb_host_alloc) -> n files in host memory,
+ * out + i*out_stride, sizes[i].  Internally pipelines H2D copy / kernels / D2H copy over chunks of the batch. */
+FPNGB_API int fpngb_encode_batch_host(const void* pixels, size_t image_stride, uint32_t n,
+                                      uint32_t w, uint32_t h, uint32_t chans, uint32_t flags,
+                                      void* out, size_t out_stride, uint32_t* sizes);
+
+/* Replaces fpng::fpng_get_info (src/fpng.h:92, src/fpng.cpp:2930-3083): container walk on the host. */
+FPNGB_API int fpngb_get_info(const void* file, uint32_t size, uint32_t* w, uint32_t* h, uint32_t* chans);
+
+/* Replaces fpng::fpng_decode_memory (src/fpng.h:108, src/fpng.cpp:3085-3139) for HOST buffers.  out_cap must be at
+ * least w*h*desired (use fpngb_get_info first).  Returns an FPNGB_DECODE_* code. */
+FPNGB_API int fpngb_decode_host(const void* file, uint32_t size, void* out, size_t out_cap,
+                                uint32_t* w, uint32_t* h, uint32_t* chans, uint32_t desired_chans);
+
+/* Batch decode of n fpng files of identical dimensions/channels resident in DEVICE memory.
+ *   d_files + i*file_stride (file_stride multiple of 16), d_file_sizes[i] bytes (host array: the container walk
+ *   needs them on the host anyway), pixels to d_out + i*out_stride.  d_status[i] receives an FPNGB_DECODE_* code
+ *   (device memory).  Enqueued on `stream`; does not synchronise. */
+FPNGB_API int fpngb_decode_batch_device(const void* d_files, size_t file_stride, const uint32_t* idat_ofs,
+                                        const uint32_t* idat_len, uint32_t n, uint32_t w, uint32_t h,
+                                        uint32_t chans_in_file, uint32_t desired_chans,
+                                        void* d_out, size_t out_stride, uint32_t* d_status, void* stream);
+
+/* Replace fpng::fpng_crc32 / fpng::fpng_adler32 (src/fpng.h:26-31).  Host buffers; computed with the device kernels. */
+FPNGB_API uint32_t fpngb_crc32(const void* data, size_t size, uint32_t prev_crc32);
+FPNGB_API uint32_t fpngb_adler32(const void* data, size_t size, uint32_t adler);
+
+/* Pinned host memory helpers for callers that want full PCIe bandwidth through the *_host entry points. */
+FPNGB_API void* fpngb_host_alloc(size_t bytes);
+FPNGB_API void fpngb_host_free(void* p);
+
+/* Number of kernels the library has launched since fpngb_init (bench.py reports it as gpu_launches). */
+FPNGB_API uint64_t fpngb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPNG_B200_H */
