@@ -197,6 +197,42 @@ void launch_crc(const CrcParams& p, uint32_t n, cudaStream_t s)
     idat_crc_kernel<<<grid, kCrcThreads, 0, s>>>(p);
 }
 
+// Adler-32 partials of a flat device buffer: CTA c covers bytes [c*64Ki, +64Ki) and writes (S1, S2) mod 65521 where
+// S1 = sum x_i and S2 = sum (len - i) x_i over its chunk; the host folds the chunks with a' = a + S1, b' = b + len*a + S2
+// (the same recurrence fpng.cpp:403-487 evaluates byte by byte).
+constexpr uint32_t kAdlerChunk = 65536;
+__global__ void __launch_bounds__(256) adler_buffer_kernel(const uint8_t* __restrict__ buf, size_t n, uint2* __restrict__ partials)
+{
+    __shared__ unsigned long long s_a[8], s_b[8];
+    const size_t c0 = (size_t)blockIdx.x * kAdlerChunk;
+    const uint32_t len = (uint32_t)min((size_t)kAdlerChunk, n - c0);
+    unsigned long long A = 0, B = 0;
+    for (uint32_t i = threadIdx.x * 16u; i < len; i += blockDim.x * 16u) {
+        uint32_t wd[4] = {0, 0, 0, 0};
+        if (i + 16u <= len) { const uint4 v = *reinterpret_cast<const uint4*>(buf + c0 + i); wd[0] = v.x; wd[1] = v.y; wd[2] = v.z; wd[3] = v.w; }
+        else for (uint32_t k = 0; i + k < len; k++) wd[k >> 2] |= (uint32_t)buf[c0 + i + k] << (8 * (k & 3));
+        uint32_t t1 = 0, t2 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { t1 = __dp4a(wd[k], 0x01010101u, t1); t2 = __dp4a(wd[k], 0x03020100u + 0x04040404u * k, t2); }
+        A += t1; B += (unsigned long long)i * t1 + t2;
+    }
+    for (int o = 16; o > 0; o >>= 1) { A += __shfl_xor_sync(0xFFFFFFFFu, A, o); B += __shfl_xor_sync(0xFFFFFFFFu, B, o); }
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = A; s_b[threadIdx.x >> 5] = B; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0, b = 0;
+        for (int i = 0; i < 8; i++) { a += s_a[i]; b += s_b[i]; }
+        partials[blockIdx.x] = make_uint2((uint32_t)(a % kAdlerMod), (uint32_t)(((unsigned long long)len * a - b) % kAdlerMod));
+    }
+}
+
+uint32_t adler_chunk_bytes() { return kAdlerChunk; }
+void launch_adler_buffer(const uint8_t* d_buf, size_t n, uint2* d_partials, cudaStream_t s)
+{
+    const uint32_t nchunks = (uint32_t)((n + kAdlerChunk - 1) / kAdlerChunk);
+    adler_buffer_kernel<<<nchunks, 256, 0, s>>>(d_buf, n, d_partials);
+}
+
 uint32_t crc_ctas_for(size_t max_file_bytes)
 {
     const size_t ntiles = (max_file_bytes + kTileBytes - 1) / kTileBytes;

@@ -139,6 +139,7 @@ struct Buffer {
 struct Context {
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the pipelined host batch path
     CodeBook* d_static_books = nullptr;          // [0] RGB, [1] RGBA
     CodeBook h_static_books[2];
     Buffer ws;                                    // kernel workspace (row tables, image state, histograms, books)
@@ -150,6 +151,35 @@ struct Context {
 
 static Context g_ctx;
 static std::mutex g_init_mu;
+
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+enum ProfSlot { kProfHist = 0, kProfHuff, kProfScan, kProfOffsets, kProfPack, kProfAdler, kProfCrc, kProfSlots };
+struct ProfSet { cudaEvent_t ev[kProfSlots + 1]; bool used[kProfSlots]; };
+static bool g_profile = false;
+static std::vector<ProfSet*> g_prof_sets;      // one per encode call since the last read
+static std::vector<ProfSet*> g_prof_free;
+
+static ProfSet* prof_begin(cudaStream_t s)
+{
+    if (!g_profile) return nullptr;
+    ProfSet* ps;
+    if (!g_prof_free.empty()) { ps = g_prof_free.back(); g_prof_free.pop_back(); }
+    else {
+        ps = new ProfSet();
+        for (int i = 0; i <= kProfSlots; i++) if (cudaEventCreate(&ps->ev[i]) != cudaSuccess) { delete ps; return nullptr; }
+    }
+    for (int i = 0; i < kProfSlots; i++) ps->used[i] = false;
+    cudaEventRecord(ps->ev[0], s);
+    g_prof_sets.push_back(ps);
+    return ps;
+}
+// records the end of slot `slot`; slots must be closed in increasing order, skipped slots stay unused
+static void prof_mark(ProfSet* ps, int slot, cudaStream_t s)
+{
+    if (!ps) return;
+    cudaEventRecord(ps->ev[slot + 1], s);
+    ps->used[slot] = true;
+}
 
 struct Workspace {
     uint32_t* row_bits; uint2* row_adler; unsigned long long* row_ofs; ImageState* st; uint32_t* hist; CodeBook* books;
@@ -232,33 +262,41 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     sp.row_bits = ws.row_bits; sp.row_adler = ws.row_adler; sp.st = ws.st; sp.hist = ws.hist;
     sp.merge_first_unit = (!two_pass && chans == 3) ? 1u : 0u;
 
+    ProfSet* ps = prof_begin(s);
     if (two_pass) {
         FPNGB_CUDA_OK(cudaMemsetAsync(ws.hist, 0, (size_t)n * 288 * 4, s));
         launch_scan(sp, n, chans, mode, true, s);
+        prof_mark(ps, kProfHist, s);
         HuffParams hp{ws.hist, ws.books, chans};
         launch_huffman_build(hp, n, s);
-        count_launch(3);
+        prof_mark(ps, kProfHuff, s);
+        count_launch(2);
     }
     launch_scan(sp, n, chans, mode, false, s);
+    prof_mark(ps, kProfScan, s);
 
     OffsetsParams op{};
     op.row_bits = ws.row_bits; op.row_ofs = ws.row_ofs; op.books = books; op.book_stride = book_stride; op.st = ws.st;
     op.out = d_out; op.out_stride = out_stride; op.sizes = d_sizes; op.w = w; op.h = h; op.chans = chans; op.flags = flags;
     make_png_header(op.png_header, w, h, chans);
     launch_offsets(op, n, s);
+    prof_mark(ps, kProfOffsets, s);
 
     PackParams pp{};
     pp.pixels = d_pixels; pp.image_stride = image_stride; pp.w = w; pp.h = h; pp.books = books; pp.book_stride = book_stride;
     pp.row_ofs = ws.row_ofs; pp.row_adler = ws.row_adler; pp.st = ws.st; pp.out = d_out; pp.out_stride = out_stride;
     launch_pack(pp, n, chans, mode, s);
+    prof_mark(ps, kProfPack, s);
 
     AdlerParams ap{ws.row_adler, ws.st, d_out, out_stride, w, h, chans};
     launch_adler_finalize(ap, n, s);
+    prof_mark(ps, kProfAdler, s);
 
     CrcParams cp{};
     cp.out = d_out; cp.out_stride = out_stride; cp.st = ws.st;
     cp.max_tiles = crc_ctas_for(max_encoded_size(w, h, chans)); cp.msg_start = kPngHeaderSize - 4; cp.init_xor = 0xFFFFFFFFu;
     launch_crc(cp, n, s);
+    prof_mark(ps, kProfCrc, s);
     count_launch(5);
     FPNGB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -331,7 +369,7 @@ int fpngb_encode_batch_device(const void* d_pixels, size_t image_stride, uint32_
     Context& c = g_ctx;
     std::lock_guard<std::mutex> lk(c.mu);
     FPNGB_CUDA_OK(cudaSetDevice(c.device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+    cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream, exactly as the caller passed it
     return encode_batch_locked(c, (const uint8_t*)d_pixels, image_stride, n, w, h, chans, flags, (uint8_t*)d_out, out_stride, d_sizes, s);
 }
 
@@ -362,6 +400,167 @@ int fpngb_encode_host(const void* pixels, uint32_t w, uint32_t h, uint32_t chans
     FPNGB_CUDA_OK(cudaStreamSynchronize(s));
     *out_size = fsize;
     return FPNGB_OK;
+}
+
+// Pipelined host-buffer batch: chunks of the batch flow H2D -> kernels -> (sizes) -> exact-size D2H through three
+// slots; chunk k+1 is enqueued before the host waits for chunk k's sizes, so copies overlap the kernels.
+int fpngb_encode_batch_host(const void* pixels, size_t image_stride, uint32_t n, uint32_t w, uint32_t h, uint32_t chans,
+                            uint32_t flags, void* out, size_t out_stride, uint32_t* sizes)
+{
+    if (!g_ctx.ready) return FPNGB_ERR_NOT_INITIALIZED;
+    if (!pixels || !out || !sizes || n == 0 || !valid_dims(w, h, chans)) return FPNGB_ERR_INVALID_ARG;
+    const size_t in_bytes = (size_t)w * h * chans, cap = max_encoded_size(w, h, chans), dstride = align_up(cap, 16);
+    if (image_stride < in_bytes) return FPNGB_ERR_INVALID_ARG;
+    if (out_stride < cap) return FPNGB_ERR_BUFFER_TOO_SMALL;
+    Context& c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    FPNGB_CUDA_OK(cudaSetDevice(c.device));
+
+    constexpr int kSlots = 3;
+    const size_t target = (size_t)64 << 20;                         // ~64 MiB of pixels per chunk
+    uint32_t per_chunk = (uint32_t)(target / in_bytes); if (per_chunk < 1) per_chunk = 1; if (per_chunk > n) per_chunk = n;
+    const size_t slot_in = align_up(per_chunk * in_bytes, 256), slot_out = per_chunk * dstride, slot_sz = align_up(per_chunk * 4, 256);
+    int rc = c.dev_in.reserve(kSlots * slot_in); if (rc) return rc;
+    rc = c.dev_out.reserve(kSlots * (slot_out + slot_sz)); if (rc) return rc;
+    rc = c.pin_small.reserve(kSlots * slot_sz); if (rc) return rc;
+    if (!c.copy_in) { FPNGB_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking)); FPNGB_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking)); }
+    cudaEvent_t ev_in[kSlots], ev_done[kSlots], ev_sizes[kSlots], ev_out[kSlots];
+    for (int i = 0; i < kSlots; i++) {
+        FPNGB_CUDA_OK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming)); FPNGB_CUDA_OK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+        FPNGB_CUDA_OK(cudaEventCreateWithFlags(&ev_sizes[i], cudaEventDisableTiming)); FPNGB_CUDA_OK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+    }
+    const uint32_t nchunks = (n + per_chunk - 1) / per_chunk;
+    const bool contiguous = image_stride == in_bytes;
+    int result = FPNGB_OK;
+
+    auto finish = [&](uint32_t k) -> int {      // exact-size D2H of chunk k's files
+        const int sl = k % kSlots;
+        const uint32_t first = k * per_chunk, cnt = (first + per_chunk <= n) ? per_chunk : n - first;
+        FPNGB_CUDA_OK(cudaEventSynchronize(ev_sizes[sl]));
+        const uint32_t* hs = (const uint32_t*)((uint8_t*)c.pin_small.p + sl * slot_sz);
+        const uint8_t* dout = (const uint8_t*)c.dev_out.p + sl * (slot_out + slot_sz);
+        for (uint32_t i = 0; i < cnt; i++) {
+            const uint32_t fs = hs[i];
+            if (fs < kPngHeaderSize + kPngTrailerSize || fs > cap) return FPNGB_ERR_INTERNAL;
+            sizes[first + i] = fs;
+            FPNGB_CUDA_OK(cudaMemcpyAsync((uint8_t*)out + (size_t)(first + i) * out_stride, dout + (size_t)i * dstride, fs, cudaMemcpyDeviceToHost, c.copy_out));
+        }
+        FPNGB_CUDA_OK(cudaEventRecord(ev_out[sl], c.copy_out));
+        return 0;
+    };
+
+    for (uint32_t k = 0; k < nchunks && result == FPNGB_OK; k++) {
+        const int sl = k % kSlots;
+        const uint32_t first = k * per_chunk, cnt = (first + per_chunk <= n) ? per_chunk : n - first;
+        if (k >= kSlots) { rc = (int)cudaEventSynchronize(ev_out[sl]); if (rc) { result = 1000 + rc; break; } }   // slot's previous files have left the device
+        uint8_t* din = (uint8_t*)c.dev_in.p + sl * slot_in;
+        uint8_t* dout = (uint8_t*)c.dev_out.p + sl * (slot_out + slot_sz);
+        uint32_t* dsz = (uint32_t*)(dout + slot_out);
+        const uint8_t* src = (const uint8_t*)pixels + (size_t)first * image_stride;
+        cudaError_t e = contiguous ? cudaMemcpyAsync(din, src, cnt * in_bytes, cudaMemcpyHostToDevice, c.copy_in)
+                                   : cudaMemcpy2DAsync(din, in_bytes, src, image_stride, in_bytes, cnt, cudaMemcpyHostToDevice, c.copy_in);
+        if (e != cudaSuccess) { result = 1000 + (int)e; break; }
+        cudaEventRecord(ev_in[sl], c.copy_in);
+        cudaStreamWaitEvent(c.stream, ev_in[sl], 0);
+        rc = encode_batch_locked(c, din, in_bytes, cnt, w, h, chans, flags, dout, dstride, dsz, c.stream);
+        if (rc) { result = rc; break; }
+        cudaEventRecord(ev_done[sl], c.stream);
+        cudaStreamWaitEvent(c.copy_out, ev_done[sl], 0);
+        cudaMemcpyAsync((uint8_t*)c.pin_small.p + sl * slot_sz, dsz, cnt * 4, cudaMemcpyDeviceToHost, c.copy_out);
+        cudaEventRecord(ev_sizes[sl], c.copy_out);
+        if (k >= 1) { rc = finish(k - 1); if (rc) { result = rc; break; } }
+    }
+    if (result == FPNGB_OK) result = finish(nchunks - 1);
+    cudaStreamSynchronize(c.copy_in); cudaStreamSynchronize(c.stream); cudaStreamSynchronize(c.copy_out);
+    for (int i = 0; i < kSlots; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_sizes[i]); cudaEventDestroy(ev_out[i]); }
+    if (result == FPNGB_OK) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) result = 1000 + (int)e; }
+    return result;
+}
+
+// Per-kernel device times (ms) averaged over the encode calls since the last read; slots in ProfSlot order:
+// hist, huffman, scan, offsets, pack, adler, crc.  Returns the number of calls averaged.
+FPNGB_API int fpngb_profile_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    g_profile = on != 0;
+    return 0;
+}
+FPNGB_API int fpngb_profile_read(float* ms, int nslots)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    double sum[kProfSlots] = {0};
+    int calls = 0;
+    for (ProfSet* ps : g_prof_sets) {
+        int last = 0;   // index of the last recorded event
+        cudaEventSynchronize(ps->ev[0]);
+        for (int i = 0; i < kProfSlots; i++) {
+            if (!ps->used[i]) continue;
+            float t = 0;
+            cudaEventSynchronize(ps->ev[i + 1]);
+            if (cudaEventElapsedTime(&t, ps->ev[last], ps->ev[i + 1]) == cudaSuccess) sum[i] += t;
+            last = i + 1;
+        }
+        calls++;
+        g_prof_free.push_back(ps);
+    }
+    g_prof_sets.clear();
+    for (int i = 0; i < nslots && i < kProfSlots; i++) ms[i] = calls ? (float)(sum[i] / calls) : 0.f;
+    return calls;
+}
+
+// fpng_crc32 / fpng_adler32 utilities (src/fpng.h:26-31) on host buffers.  Buffers of at least 4 KiB go through the
+// device kernels; shorter ones (chunk headers, IHDR) use the host table that the container code needs anyway.
+uint32_t fpngb_crc32(const void* data, size_t size, uint32_t prev)
+{
+    if (!data || !size) return prev;
+    if (!g_ctx.ready || size < 4096 || size > 0xFFFFFF00ull) return host_crc32(data, size, prev);
+    Context& c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (cudaSetDevice(c.device) != cudaSuccess) return 0;
+    const size_t padded = align_up(size + 16, 16);
+    if (c.dev_in.reserve(padded + 256)) return 0;
+    ImageState hst{}; hst.zsize = (uint32_t)size - kPngHeaderSize;       // kernel computes L = 58 + zsize = size
+    ImageState* dst = (ImageState*)((uint8_t*)c.dev_in.p + padded);
+    cudaMemcpyAsync(c.dev_in.p, data, size, cudaMemcpyHostToDevice, c.stream);
+    cudaMemcpyAsync(dst, &hst, sizeof hst, cudaMemcpyHostToDevice, c.stream);
+    CrcParams cp{};
+    cp.out = (uint8_t*)c.dev_in.p; cp.out_stride = 0; cp.st = dst; cp.max_tiles = crc_ctas_for(size); cp.msg_start = 0; cp.init_xor = ~prev;
+    launch_crc(cp, 1, c.stream);
+    count_launch(1);
+    uint8_t be[4] = {0, 0, 0, 0};
+    cudaMemcpyAsync(be, (uint8_t*)c.dev_in.p + size, 4, cudaMemcpyDeviceToHost, c.stream);
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) return 0;
+    return ((uint32_t)be[0] << 24) | ((uint32_t)be[1] << 16) | ((uint32_t)be[2] << 8) | be[3];
+}
+
+uint32_t fpngb_adler32(const void* data, size_t size, uint32_t adler)
+{
+    uint32_t a = adler & 0xFFFF, b = adler >> 16;
+    if (!data || !size) return adler;
+    if (!g_ctx.ready || size < 4096) {
+        const uint8_t* p = (const uint8_t*)data;
+        for (size_t i = 0; i < size; i++) { a = (a + p[i]) % kAdlerMod; b = (b + a) % kAdlerMod; }
+        return (b << 16) | a;
+    }
+    Context& c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (cudaSetDevice(c.device) != cudaSuccess) return 0;
+    const size_t padded = align_up(size, 256), nchunks = (size + adler_chunk_bytes() - 1) / adler_chunk_bytes();
+    if (c.dev_in.reserve(padded + nchunks * 8)) return 0;
+    uint2* dpart = (uint2*)((uint8_t*)c.dev_in.p + padded);
+    std::vector<uint2> part(nchunks);
+    cudaMemcpyAsync(c.dev_in.p, data, size, cudaMemcpyHostToDevice, c.stream);
+    launch_adler_buffer((const uint8_t*)c.dev_in.p, size, dpart, c.stream);
+    count_launch(1);
+    cudaMemcpyAsync(part.data(), dpart, nchunks * 8, cudaMemcpyDeviceToHost, c.stream);
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) return 0;
+    unsigned long long A = a, B = b;
+    for (size_t i = 0; i < nchunks; i++) {
+        const unsigned long long len = (i + 1 < nchunks) ? adler_chunk_bytes() : size - i * adler_chunk_bytes();
+        B = (B + (len % kAdlerMod) * A + part[i].y) % kAdlerMod;
+        A = (A + part[i].x) % kAdlerMod;
+    }
+    return (uint32_t)((B << 16) | A);
 }
 
 void* fpngb_host_alloc(size_t bytes)

@@ -65,7 +65,7 @@ FPNGB_API int fpngb_encode_host(const void* pixels, uint32_t w, uint32_t h, uint
  *   d_pixels + i*image_stride : image i (tightly packed rows)
  *   d_out    + i*out_stride   : file i; out_stride >= fpngb_max_encoded_size(), multiple of 16; d_out 16-byte aligned
  *   d_sizes[i]                : file size in bytes (device memory, n x uint32)
- * All kernels are enqueued on `stream` (a cudaStream_t; NULL = the library's own stream); the call does not
+ * All kernels are enqueued on `stream` (a cudaStream_t; NULL = the CUDA default stream); the call does not
  * synchronise.  This is the path bench.py times; it is what one rank runs on its shard of a multi-GPU batch. */
 FPNGB_API int fpngb_encode_batch_device(const void* d_pixels, size_t image_stride, uint32_t n,
                                         uint32_t w, uint32_t h, uint32_t chans, uint32_t flags,

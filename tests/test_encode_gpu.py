@@ -1,0 +1,148 @@
+"""GPU parity tests of the encode hot path, through the C ABI (fpngb_encode_host / fpngb_encode_batch_device /
+fpngb_encode_batch_host).  Bit-exact bar: the CUDA output must equal the oracle's bytes (which equal the reference's),
+match the committed golden vectors, and round-trip through the reference decoder, lodepng and stb_image.
+Mirrors the reference's own test strategy (src/fpng_test.cpp:1237-1445 round trips, 381-682 fuzz families, -u, -s)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import imagegen
+from common import golden_vectors, sha
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(1, 1), (1, 9), (2, 2), (5, 3), (15, 2), (16, 2), (20, 1), (24, 1), (63, 3), (64, 3), (65, 3), (85, 2), (86, 2), (127, 5),
+          (128, 4), (129, 6), (255, 3), (256, 3), (257, 33), (340, 5), (512, 64), (687, 41), (1000, 3), (2049, 2)]
+
+
+@pytest.mark.parametrize("kind", ["g0", "g1", "g2", "runs", "mut", "zero"])
+@pytest.mark.parametrize("chans", [3, 4])
+def test_encode_byte_exact_vs_oracle(gpu, oracle, kind, chans):
+    for i, (w, h) in enumerate(SHAPES):
+        img = imagegen.make(kind, w, h, chans, 100 + i)
+        for flags in (0, gpu.FPNG_ENCODE_SLOWER, gpu.FPNG_FORCE_UNCOMPRESSED):
+            ok, png = gpu.fpng_encode_image_to_memory(img, w, h, chans, flags)
+            assert ok
+            exp = oracle.encode(img, w, h, chans, flags)
+            assert png == exp, (kind, w, h, chans, flags, len(png), len(exp))
+
+
+def test_encode_matches_golden_vectors(gpu):
+    for v in golden_vectors():
+        img = imagegen.make(v["kind"], v["w"], v["h"], v["chans"], v["index"])
+        ok, png = gpu.fpng_encode_image_to_memory(img, v["w"], v["h"], v["chans"], v["flags"])
+        assert ok and len(png) == v["size"] and sha(png) == v["png_sha256"], v
+
+
+def test_encode_round_trips_through_independent_decoders(gpu, ref):
+    for (kind, w, h, c) in (("g1", 301, 57, 3), ("g1", 300, 57, 4), ("runs", 1024, 9, 4), ("g2", 77, 31, 3), ("g0", 640, 48, 4), ("mut", 333, 21, 3)):
+        img = imagegen.make(kind, w, h, c, 5)
+        for flags in (0, 1, 2):
+            ok, png = gpu.fpng_encode_image_to_memory(img, w, h, c, flags)
+            assert ok
+            st, px, ww, hh, cc = ref.decode(png, c)                       # the reference's own decoder
+            assert st == 0 and (ww, hh, cc) == (w, h, c) and np.array_equal(px, img.reshape(-1))
+            err, px, ww, hh = ref.lodepng_decode(png, c)                    # checks IDAT CRC-32 and Adler-32
+            assert err == 0 and np.array_equal(px, img.reshape(-1))
+            comp, px, ww, hh = ref.stb_decode(png, c)
+            assert comp == c and np.array_equal(px, img.reshape(-1))
+            assert png == ref.encode(img, w, h, c, flags)                   # byte-exact with the reference encoder
+
+
+def test_encode_python_zlib_and_crc(gpu):
+    import struct
+    import zlib
+    img = imagegen.make("g1", 200, 50, 4, 9)
+    ok, png = gpu.fpng_encode_image_to_memory(img, 200, 50, 4, 0)
+    assert ok and png[:8] == b"\x89PNG\r\n\x1a\n"
+    idat_len = struct.unpack(">I", png[50:54])[0]
+    assert png[54:58] == b"IDAT" and len(png) == 58 + idat_len + 16
+    raw = zlib.decompress(png[58:58 + idat_len])
+    assert len(raw) == (200 * 4 + 1) * 50
+    assert zlib.crc32(png[54:58 + idat_len]) == struct.unpack(">I", png[58 + idat_len:62 + idat_len])[0]
+
+
+def test_encode_invalid_arguments(gpu):
+    # src/fpng.cpp:1670-1680: returns false
+    assert gpu.fpng_encode_image_to_memory(bytes(12), 0, 2, 3)[0] is False
+    assert gpu.fpng_encode_image_to_memory(bytes(12), 2, 2, 5)[0] is False
+    assert gpu.fpng_encode_image_to_memory(bytes(11), 2, 2, 3)[0] is False
+    assert gpu.fpng_encode_image_to_memory(bytes(12), (1 << 24) + 1, 1, 3)[0] is False
+
+
+def test_batch_device_api(gpu, oracle):
+    import torch
+    for (w, h, c, n, flags) in ((640, 36, 3, 5, 0), (256, 40, 4, 7, 0), (255, 17, 3, 4, 0), (130, 20, 4, 3, 1), (96, 8, 3, 3, 2)):
+        imgs = np.stack([imagegen.make(["g1", "g0", "runs", "g2"][i % 4], w, h, c, i) for i in range(n)])
+        t = torch.from_numpy(imgs).cuda()
+        out, sizes = gpu.encode_batch_device(t, flags)
+        torch.cuda.synchronize()
+        sizes = sizes.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        out = out.cpu().numpy()
+        for i in range(n):
+            assert bytes(out[i, : sizes[i]]) == oracle.encode(imgs[i], w, h, c, flags), (w, h, c, i, flags)
+
+
+def test_batch_device_unaligned_views(gpu, oracle):
+    """Images whose base address is not 16/4-byte aligned take the byte-load kernels."""
+    import torch
+    w, h, c, n = 37, 11, 3, 3
+    imgs = np.stack([imagegen.make("g1", w, h, c, i) for i in range(n)])
+    buf = torch.zeros(n * w * h * c + 1, dtype=torch.uint8, device="cuda")
+    buf[1:] = torch.from_numpy(imgs.reshape(-1)).cuda()
+    view = buf[1:].view(n, h, w, c)
+    out, sizes = gpu.encode_batch_device(view, 0)
+    torch.cuda.synchronize()
+    sizes = sizes.cpu().numpy().astype(np.int64)
+    out = out.cpu().numpy()
+    for i in range(n):
+        assert bytes(out[i, : sizes[i]]) == oracle.encode(imgs[i], w, h, c, 0)
+
+
+def test_batch_host_api(gpu, oracle):
+    from fpng_b200._lib import lib
+    L = lib()
+    w, h, c, n = 512, 300, 4, 9
+    imgs = np.stack([imagegen.make(["g1", "g0", "g2"][i % 3], w, h, c, i) for i in range(n)])
+    stride = gpu.max_encoded_size(w, h, c)
+    out = np.zeros((n, stride), np.uint8)
+    sizes = np.zeros(n, np.uint32)
+    rc = L.fpngb_encode_batch_host(imgs.ctypes.data_as(C.c_void_p), w * h * c, n, w, h, c, 0, out.ctypes.data_as(C.c_void_p), stride,
+                                   sizes.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    for i in range(n):
+        assert bytes(out[i, : sizes[i]]) == oracle.encode(imgs[i], w, h, c, 0), i
+
+
+def test_full_size_configs_properties(gpu, ref):
+    """BASELINE.json shapes at full size: size-independent checks (decode round trip, checksum of checksums)."""
+    import torch
+    import zlib
+    for (w, h, c, flags) in ((1920, 1080, 3, 0), (3840, 2160, 4, 0), (2048, 2048, 3, 1), (512, 512, 4, 0)):
+        imgs = np.stack([imagegen.make(k, w, h, c, 3) for k in ("g1", "g0")])
+        out, sizes = gpu.encode_batch_device(torch.from_numpy(imgs).cuda(), flags)
+        torch.cuda.synchronize()
+        sizes = sizes.cpu().numpy().astype(np.int64)
+        out = out.cpu().numpy()
+        for i in range(2):
+            png = bytes(out[i, : sizes[i]])
+            raw = zlib.decompress(png[58:-16])                      # verifies Adler-32
+            assert zlib.crc32(png[54:-16]) == int.from_bytes(png[-16:-12], "big")
+            assert len(raw) == (w * c + 1) * h
+            st, px, *_ = ref.decode(png, c)
+            assert st == 0 and np.array_equal(px, imgs[i].reshape(-1))
+            if flags == 0:
+                assert png == ref.encode(imgs[i], w, h, c, flags)
+
+
+def test_checksum_utilities(gpu, oracle):
+    rs = np.random.RandomState(1)
+    for n in (1, 3, 4, 57, 4095, 4096, 4097, 65536, 65537, 1 << 20, (1 << 20) + 13, 5_000_001):
+        d = rs.randint(0, 256, size=n, dtype=np.uint8)
+        assert gpu.fpng_crc32(d) == oracle.crc32(d), n
+        assert gpu.fpng_adler32(d) == oracle.adler32(d), n
+        assert gpu.fpng_crc32(d, 0x12345678) == oracle.crc32(d, 0x12345678), n
+        assert gpu.fpng_adler32(d, 0x00030002) == oracle.adler32(d, 0x00030002), n
+    assert gpu.fpng_crc32(b"123456789") == 0xCBF43926
+    assert gpu.fpng_adler32(b"Wikipedia") == 0x11E60398
