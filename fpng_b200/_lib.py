@@ -40,6 +40,11 @@ def lib() -> C.CDLL:
     L.fpngb_get_info.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, u32p]
     L.fpngb_decode_host.restype = C.c_int
     L.fpngb_decode_host.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, u32p, u32p, u32p, C.c_uint32]
+    L.fpngb_get_info_ex.restype = C.c_int
+    L.fpngb_get_info_ex.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, u32p, u32p, u32p]
+    L.fpngb_decode_batch_device.restype = C.c_int
+    L.fpngb_decode_batch_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                            C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.fpngb_crc32.restype = C.c_uint32
     L.fpngb_crc32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
     L.fpngb_adler32.restype = C.c_uint32

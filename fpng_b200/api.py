@@ -147,3 +147,58 @@ def encode_batch_device(images, flags: int = 0, out=None, sizes=None, stream=Non
                                          sizes.data_ptr(), s)
     check(rc, "encode_batch_device")
     return out, sizes
+
+
+def get_info_ex(data):
+    """fpng_get_info plus (idat_ofs, idat_len): the host-side container walk (src/fpng.cpp:2930-3077)."""
+    a = _u8(data)
+    w, h, c, o, l = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    st = lib().fpngb_get_info_ex(a.ctypes.data_as(C.c_void_p), a.size, C.byref(w), C.byref(h), C.byref(c), C.byref(o), C.byref(l))
+    return st, w.value, h.value, c.value, o.value, l.value
+
+
+def pack_files_for_device(files, device=None):
+    """Container-walks a list of fpng files (bytes) of identical dimensions on the host and packs them into one device
+    tensor [n, stride].  Returns (tensor, stride, sizes, idat_ofs, idat_len, w, h, chans)."""
+    import torch
+
+    infos = [get_info_ex(f) for f in files]
+    for st, *_ in infos:
+        if st != 0:
+            raise FpngB200Error(f"pack_files_for_device: fpng_get_info returned {st}")
+    w, h, c = infos[0][1:4]
+    if any(i[1:4] != (w, h, c) for i in infos):
+        raise FpngB200Error("pack_files_for_device: files differ in dimensions/channels")
+    stride = (max(len(f) for f in files) + 16 + 15) // 16 * 16
+    host = np.zeros((len(files), stride), dtype=np.uint8)
+    for i, f in enumerate(files):
+        host[i, : len(f)] = np.frombuffer(f, dtype=np.uint8)
+    t = torch.from_numpy(host)
+    if device is not None:
+        t = t.to(device)
+    sizes = np.array([len(f) for f in files], dtype=np.uint32)
+    ofs = np.array([i[4] for i in infos], dtype=np.uint32)
+    lens = np.array([i[5] for i in infos], dtype=np.uint32)
+    return t, stride, sizes, ofs, lens, w, h, c
+
+
+def decode_batch_device(files_dev, sizes, idat_ofs, idat_len, w: int, h: int, chans_in_file: int, desired_channels: int,
+                        out=None, status=None, stream=None):
+    """Decode n fpng files resident on the device (tensor [n, stride] uint8). Returns (pixels [n, h, w, desired], status [n])."""
+    import torch
+
+    assert files_dev.is_cuda and files_dev.dtype == torch.uint8 and files_dev.dim() == 2 and files_dev.is_contiguous()
+    n = files_dev.shape[0]
+    if out is None:
+        out = torch.empty((n, h, w, desired_channels), dtype=torch.uint8, device=files_dev.device)
+    if status is None:
+        status = torch.empty((n,), dtype=torch.int32, device=files_dev.device)
+    s = stream if stream is not None else torch.cuda.current_stream(files_dev.device).cuda_stream
+    sizes = np.ascontiguousarray(sizes, dtype=np.uint32); idat_ofs = np.ascontiguousarray(idat_ofs, dtype=np.uint32)
+    idat_len = np.ascontiguousarray(idat_len, dtype=np.uint32)
+    rc = lib().fpngb_decode_batch_device(files_dev.data_ptr(), files_dev.stride(0), sizes.ctypes.data_as(C.c_void_p),
+                                         idat_ofs.ctypes.data_as(C.c_void_p), idat_len.ctypes.data_as(C.c_void_p), n, w, h,
+                                         chans_in_file, desired_channels, out.data_ptr(), h * w * desired_channels,
+                                         status.data_ptr(), s)
+    check(rc, "decode_batch_device")
+    return out, status

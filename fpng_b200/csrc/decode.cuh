@@ -1,0 +1,35 @@
+// fpng_b200/csrc/decode.cuh -- parameter blocks of the decode kernels.
+#pragma once
+#include "common.cuh"
+
+namespace fpngb {
+
+constexpr int kDecThreads = 512;            // subsequences decoded concurrently per file (one CTA per file)
+constexpr uint32_t kSubBits = 512;          // bits per subsequence (>> longest token: 12 + 5 + 1 bits)
+
+struct FileDesc {                           // filled by the host container walk (fpng.cpp:2930-3077)
+    uint32_t file_size, idat_ofs, idat_len, pad_;
+};
+
+struct DecodeState {
+    uint32_t status;                        // 0 ok, 1 -> FPNG_DECODE_NOT_FPNG
+    uint32_t stored;                        // stored-block file
+    unsigned long long token_start;         // bit offset (from the zlib stream start) of the first token
+    unsigned long long out_bytes;           // filtered-stream bytes produced
+    unsigned long long end_byte;            // bytes consumed up to and including the padded EOB
+};
+
+struct DecodeParams {
+    const uint8_t* d_files; size_t file_stride;
+    const FileDesc* files;                  // [n] device
+    DecodeState* state;                     // [n]
+    uint16_t* luts;                         // [n][4096]  sym | len << 9
+    uint8_t* delta; uint32_t delta_pitch;   // [n][h][pitch] filtered rows without the filter byte
+    uint8_t* d_out; size_t out_stride;
+    uint32_t* d_status;                     // [n] FPNG_DECODE_* codes
+    uint32_t w, h, chans;
+};
+
+void launch_decode(const DecodeParams& p, uint32_t n, uint32_t desired, cudaStream_t s);
+
+}  // namespace fpngb

@@ -1,7 +1,10 @@
 // fpng_b200/csrc/decode_api.cu -- container walk (host) and decode entry points of the C ABI.
 #include "../../include/fpng_b200.h"
 #include "kernels.cuh"
+#include "decode.cuh"
+#include "runtime.h"
 #include <string.h>
+#include <vector>
 
 namespace fpngb {
 
@@ -56,9 +59,100 @@ int container_info(const uint8_t* f, uint32_t size, uint32_t* w, uint32_t* h, ui
 
 }  // namespace fpngb
 
+namespace fpngb {
+
+static Buffer g_dec_ws;        // FileDesc[n] | DecodeState[n] | luts | delta scratch
+static Buffer g_dec_pin;       // pinned staging for the FileDesc upload / status download
+
+// Enqueue the decode pipeline for n files already resident on the device.  Caller holds context().mu.
+static int decode_batch_locked(const uint8_t* d_files, size_t file_stride, const FileDesc* h_files, uint32_t n, uint32_t w, uint32_t h,
+                               uint32_t chans, uint32_t desired, uint8_t* d_out, size_t out_stride, uint32_t* d_status, cudaStream_t s)
+{
+    const uint32_t bpl = w * chans, pitch = (uint32_t)align_up(bpl, 16);
+    size_t o = 0;
+    const size_t o_files = o; o = align_up(o + (size_t)n * sizeof(FileDesc), 256);
+    const size_t o_state = o; o = align_up(o + (size_t)n * sizeof(DecodeState), 256);
+    const size_t o_luts = o; o = align_up(o + (size_t)n * 4096 * 2, 256);
+    const size_t o_delta = o; o = align_up(o + (size_t)n * pitch * h + 64, 256);
+    int rc = g_dec_ws.reserve(o); if (rc) return rc;
+    g_dec_pin.pinned = true;
+    rc = g_dec_pin.reserve((size_t)n * sizeof(FileDesc)); if (rc) return rc;
+    // the pinned staging buffer may still be in flight from the previous call on another stream: wait for it
+    static cudaEvent_t staged = nullptr;
+    if (!staged) FPNGB_CUDA_OK(cudaEventCreateWithFlags(&staged, cudaEventDisableTiming));
+    else FPNGB_CUDA_OK(cudaEventSynchronize(staged));
+    memcpy(g_dec_pin.p, h_files, (size_t)n * sizeof(FileDesc));
+    uint8_t* b = (uint8_t*)g_dec_ws.p;
+    FPNGB_CUDA_OK(cudaMemcpyAsync(b + o_files, g_dec_pin.p, (size_t)n * sizeof(FileDesc), cudaMemcpyHostToDevice, s));
+    FPNGB_CUDA_OK(cudaEventRecord(staged, s));
+    DecodeParams p{};
+    p.d_files = d_files; p.file_stride = file_stride; p.files = (const FileDesc*)(b + o_files); p.state = (DecodeState*)(b + o_state);
+    p.luts = (uint16_t*)(b + o_luts); p.delta = b + o_delta; p.delta_pitch = pitch; p.d_out = d_out; p.out_stride = out_stride;
+    p.d_status = d_status; p.w = w; p.h = h; p.chans = chans;
+    launch_decode(p, n, desired, s);
+    count_launch(5);
+    FPNGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fpngb
+
 using namespace fpngb;
 
 extern "C" {
+
+int fpngb_decode_batch_device(const void* d_files, size_t file_stride, const uint32_t* file_sizes, const uint32_t* idat_ofs,
+                              const uint32_t* idat_len, uint32_t n, uint32_t w, uint32_t h, uint32_t chans_in_file,
+                              uint32_t desired_chans, void* d_out, size_t out_stride, uint32_t* d_status, void* stream)
+{
+    Context& c = context();
+    if (!c.ready) return FPNGB_ERR_NOT_INITIALIZED;
+    if (!d_files || !file_sizes || !idat_ofs || !idat_len || !d_out || !d_status || n == 0 || n > 65535) return FPNGB_ERR_INVALID_ARG;
+    if ((chans_in_file != 3 && chans_in_file != 4) || (desired_chans != 3 && desired_chans != 4) || !w || !h) return FPNGB_ERR_INVALID_ARG;
+    if ((uint64_t)w * h * desired_chans > 0xFFFFFFFFull || out_stride < (size_t)w * h * desired_chans) return FPNGB_ERR_BUFFER_TOO_SMALL;
+    if (file_stride % 4 || (uintptr_t)d_files % 4) return FPNGB_ERR_ALIGNMENT;
+    std::vector<FileDesc> fds(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if ((uint64_t)idat_ofs[i] + 8 + idat_len[i] + 4 > file_sizes[i] || file_sizes[i] > file_stride) return FPNGB_ERR_INVALID_ARG;
+        fds[i] = FileDesc{file_sizes[i], idat_ofs[i], idat_len[i], 0};
+    }
+    std::lock_guard<std::mutex> lk(c.mu);
+    FPNGB_CUDA_OK(cudaSetDevice(c.device));
+    return decode_batch_locked((const uint8_t*)d_files, file_stride, fds.data(), n, w, h, chans_in_file, desired_chans, (uint8_t*)d_out,
+                               out_stride, d_status, (cudaStream_t)stream);
+}
+
+int fpngb_decode_host(const void* file, uint32_t size, void* out, size_t out_cap, uint32_t* w, uint32_t* h, uint32_t* chans, uint32_t desired)
+{
+    uint32_t ww = 0, hh = 0, cc = 0, idat_ofs = 0, idat_len = 0;
+    if (w) *w = 0; if (h) *h = 0; if (chans) *chans = 0;
+    if (!file || !size || !out || (desired != 3 && desired != 4)) return FPNGB_DECODE_INVALID_ARG;     // fpng.cpp:3092-3096
+    const int st = container_info((const uint8_t*)file, size, &ww, &hh, &cc, &idat_ofs, &idat_len);
+    if (w) *w = ww; if (h) *h = hh; if (chans) *chans = cc;
+    if (st) return st;
+    const uint64_t need = (uint64_t)ww * hh * desired;
+    if (need > 0xFFFFFFFFull) return FPNGB_DECODE_FAILED_DIMENSIONS_TOO_LARGE;                          // fpng.cpp:3103-3105
+    if (out_cap < need) return FPNGB_DECODE_INVALID_ARG;
+    Context& c = context();
+    if (!c.ready) return FPNGB_DECODE_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (cudaSetDevice(c.device) != cudaSuccess) return FPNGB_DECODE_INVALID_ARG;
+    const size_t fstride = align_up((size_t)size + 16, 16);
+    if (c.dev_in.reserve(fstride) || c.dev_out.reserve(align_up(need, 16) + 64)) return FPNGB_DECODE_INVALID_ARG;
+    uint32_t* d_status = (uint32_t*)((uint8_t*)c.dev_out.p + align_up(need, 16));
+    cudaStream_t s = c.stream;
+    cudaMemcpyAsync(c.dev_in.p, file, size, cudaMemcpyHostToDevice, s);
+    FileDesc fd{size, idat_ofs, idat_len, 0};
+    if (decode_batch_locked((const uint8_t*)c.dev_in.p, fstride, &fd, 1, ww, hh, cc, desired, (uint8_t*)c.dev_out.p, align_up(need, 16), d_status, s))
+        return FPNGB_DECODE_INVALID_ARG;
+    uint32_t* h_status = (uint32_t*)c.pin_small.p;
+    cudaMemcpyAsync(h_status, d_status, 4, cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return FPNGB_DECODE_INVALID_ARG;
+    if (*h_status) return FPNGB_DECODE_NOT_FPNG;                                                        // fpng.cpp:3131-3136
+    cudaMemcpyAsync(out, c.dev_out.p, need, cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return FPNGB_DECODE_INVALID_ARG;
+    return FPNGB_DECODE_SUCCESS;
+}
 
 int fpngb_get_info(const void* file, uint32_t size, uint32_t* w, uint32_t* h, uint32_t* chans)
 {
@@ -67,6 +161,12 @@ int fpngb_get_info(const void* file, uint32_t size, uint32_t* w, uint32_t* h, ui
     const int st = container_info((const uint8_t*)file, size, &ww, &hh, &cc, &a, &b);
     if (w) *w = ww; if (h) *h = hh; if (chans) *chans = cc;
     return st;
+}
+
+int fpngb_get_info_ex(const void* file, uint32_t size, uint32_t* w, uint32_t* h, uint32_t* chans, uint32_t* idat_ofs, uint32_t* idat_len)
+{
+    if (!file || !w || !h || !chans || !idat_ofs || !idat_len) return FPNGB_DECODE_INVALID_ARG;
+    return container_info((const uint8_t*)file, size, w, h, chans, idat_ofs, idat_len);
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "row_walk.cuh"
 #include "static_tables.h"
+#include "runtime.h"
 
 #include <atomic>
 #include <mutex>
@@ -123,34 +124,9 @@ static bool build_static_book(CodeBook& cb, const uint8_t* hdr, uint32_t nbytes,
 // ---------------------------------------------------------------------------------------------------------
 // Context
 // ---------------------------------------------------------------------------------------------------------
-struct Buffer {
-    void* p = nullptr; size_t cap = 0; bool pinned = false;
-    int reserve(size_t n)
-    {
-        if (n <= cap) return 0;
-        if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
-        n = (n + (1u << 20)) & ~((size_t)(1u << 20) - 1);
-        FPNGB_CUDA_OK(pinned ? cudaMallocHost(&p, n) : cudaMalloc(&p, n));
-        cap = n;
-        return 0;
-    }
-};
-
-struct Context {
-    int device = -1;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the pipelined host batch path
-    CodeBook* d_static_books = nullptr;          // [0] RGB, [1] RGBA
-    CodeBook h_static_books[2];
-    Buffer ws;                                    // kernel workspace (row tables, image state, histograms, books)
-    Buffer dev_in, dev_out;                       // staging for the *_host entry points
-    Buffer pin_small;                             // pinned scratch for sizes / status words
-    std::mutex mu;                                // the *_host entry points and the workspace are serialised
-    bool ready = false;
-};
-
 static Context g_ctx;
 static std::mutex g_init_mu;
+Context& context() { return g_ctx; }
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
 enum ProfSlot { kProfHist = 0, kProfHuff, kProfScan, kProfOffsets, kProfPack, kProfAdler, kProfCrc, kProfSlots };
@@ -185,7 +161,6 @@ struct Workspace {
     uint32_t* row_bits; uint2* row_adler; unsigned long long* row_ofs; ImageState* st; uint32_t* hist; CodeBook* books;
 };
 
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int carve_workspace(Context& c, uint32_t n, uint32_t h, bool two_pass, Workspace& w)
 {

@@ -1,0 +1,39 @@
+// fpng_b200/csrc/runtime.h -- host runtime state shared by host_api.cu and decode_api.cu.
+#pragma once
+#include "common.cuh"
+#include <mutex>
+
+namespace fpngb {
+
+struct Buffer {
+    void* p = nullptr; size_t cap = 0; bool pinned = false;
+    int reserve(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
+        n = (n + (1u << 20)) & ~((size_t)(1u << 20) - 1);
+        FPNGB_CUDA_OK(pinned ? cudaMallocHost(&p, n) : cudaMalloc(&p, n));
+        cap = n;
+        return 0;
+    }
+};
+
+struct Context {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the pipelined host batch path
+    CodeBook* d_static_books = nullptr;          // [0] RGB, [1] RGBA
+    CodeBook h_static_books[2];
+    Buffer ws;                                    // kernel workspace (row tables, image state, histograms, books)
+    Buffer dev_in, dev_out;                       // staging for the *_host entry points
+    Buffer pin_small;                             // pinned scratch for sizes / status words
+    std::mutex mu;                                // the *_host entry points and the workspace are serialised
+    bool ready = false;
+};
+
+
+Context& context();
+void count_launch(uint64_t n);
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace fpngb

@@ -85,14 +85,22 @@ FPNGB_API int fpngb_get_info(const void* file, uint32_t size, uint32_t* w, uint3
 FPNGB_API int fpngb_decode_host(const void* file, uint32_t size, void* out, size_t out_cap,
                                 uint32_t* w, uint32_t* h, uint32_t* chans, uint32_t desired_chans);
 
-/* Batch decode of n fpng files of identical dimensions/channels resident in DEVICE memory.
- *   d_files + i*file_stride (file_stride multiple of 16), d_file_sizes[i] bytes (host array: the container walk
- *   needs them on the host anyway), pixels to d_out + i*out_stride.  d_status[i] receives an FPNGB_DECODE_* code
- *   (device memory).  Enqueued on `stream`; does not synchronise. */
-FPNGB_API int fpngb_decode_batch_device(const void* d_files, size_t file_stride, const uint32_t* idat_ofs,
-                                        const uint32_t* idat_len, uint32_t n, uint32_t w, uint32_t h,
-                                        uint32_t chans_in_file, uint32_t desired_chans,
+/* Batch decode of n fpng files of identical dimensions/channels resident in DEVICE memory (the device-side
+ * counterpart of fpng_decode_memory; what bench.py's decode leg and one rank of a multi-GPU decode run).
+ *   d_files + i*file_stride   : file i (file_stride multiple of 4, >= file size + 16; d_files 4-byte aligned)
+ *   file_sizes/idat_ofs/idat_len[i] : HOST arrays from the container walk (fpngb_get_info_ex) -- chunk parsing stays on
+ *                               the host exactly where the reference does it (src/fpng.cpp:2930-3077)
+ *   d_out + i*out_stride      : w*h*desired_chans pixels of file i
+ *   d_status[i]               : FPNGB_DECODE_SUCCESS or FPNGB_DECODE_NOT_FPNG (device memory, n x uint32)
+ * Enqueued on `stream` (NULL = the CUDA default stream); does not synchronise. */
+FPNGB_API int fpngb_decode_batch_device(const void* d_files, size_t file_stride, const uint32_t* file_sizes,
+                                        const uint32_t* idat_ofs, const uint32_t* idat_len, uint32_t n,
+                                        uint32_t w, uint32_t h, uint32_t chans_in_file, uint32_t desired_chans,
                                         void* d_out, size_t out_stride, uint32_t* d_status, void* stream);
+
+/* fpngb_get_info plus the location of the IDAT chunk (offset of the chunk's length field, and the IDAT length). */
+FPNGB_API int fpngb_get_info_ex(const void* file, uint32_t size, uint32_t* w, uint32_t* h, uint32_t* chans,
+                                uint32_t* idat_ofs, uint32_t* idat_len);
 
 /* Replace fpng::fpng_crc32 / fpng::fpng_adler32 (src/fpng.h:26-31).  Host buffers; computed with the device kernels. */
 FPNGB_API uint32_t fpngb_crc32(const void* data, size_t size, uint32_t prev_crc32);
