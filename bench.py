@@ -85,8 +85,9 @@ def make_device_batch(wl, kind: str, n: int, device, first_index: int = 0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): the sampler runs
+    from before the warm-up, every sample is time-stamped, and only samples inside [t0, t1] are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
@@ -95,35 +96,46 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
+        """t0/t1: time.time() bounds of the timed region."""
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in out.strip().splitlines():
             f = [t.strip() for t in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [r for r in rows if t0 - 0.02 <= r[0] <= t1 + 0.02]
+        note = "samples inside the timed region"
+        if not inside:   # timed region shorter than the sampling period: take the closest samples under the same load
+            inside = sorted(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:3]
+            note = "timed region shorter than the sampling period; nearest samples (warm-up/timed loop)"
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median([r[1] for r in inside]) if inside else None,
+                "sm_max_mhz": max([r[2] for r in inside]) if inside else None,
+                "samples": len(inside), "reasons": sorted(reasons), "note": note}
 
 
 def measured_peak():
@@ -135,41 +147,83 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_run(wl, kind: str, seconds: float, steps: int = 1):
-    """Times the UNMODIFIED reference encoder (oracle/_ref) on all host cores over a bounded sample of the workload.
-    Returns (values MP/s per step, cores, sample description, kind)."""
+def host_cores() -> int:
+    """Usable host threads: scheduler affinity capped by the cgroup CPU quota (the box may expose more CPUs than it grants)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def _timed_pool(work_once, cores: int, seconds: float):
+    """Runs work_once(k) repeatedly on `cores` threads until `seconds` elapse; returns (calls completed, elapsed)."""
     from concurrent.futures import ThreadPoolExecutor
 
+    deadline = time.perf_counter() + seconds
+    counts = [0] * cores
+
+    def loop(k):
+        while time.perf_counter() < deadline:
+            work_once(k)
+            counts[k] += 1
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(loop, range(cores)))
+    return sum(counts), time.perf_counter() - t0
+
+
+def cpu_reference_run(wl, kind: str, seconds: float, steps: int = 1):
+    """Times the UNMODIFIED reference encoder (oracle/_ref; the oracle port if it is not built) on all usable host threads,
+    each encoding whole images of the workload sample until `seconds` elapse.  Returns (MP/s per step, cores, sample, kind)."""
     from oracle.pyoracle import Oracle, Ref
 
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     w, h, c, flags = wl["w"], wl["h"], wl["chans"], wl["flags"]
     use_ref = Ref.available()
     enc = Ref() if use_ref else Oracle()
-    imgs = [np.ascontiguousarray(workload_image(wl, kind, i)) for i in range(min(cores, wl["images"]))]
-    # calibrate: one image on one core
-    t0 = time.perf_counter()
-    (enc.encode_discard(imgs[0], w, h, c, flags, 1) if use_ref else enc.encode(imgs[0], w, h, c, flags))
-    t1 = max(time.perf_counter() - t0, 1e-4)
-    reps = max(1, int(seconds / t1))
+    imgs = [np.ascontiguousarray(workload_image(wl, kind, i)) for i in range(min(cores, 16, wl["images"]))]
 
-    def work(k):
+    def once(k):
         img = imgs[k % len(imgs)]
         if use_ref:
-            enc.encode_discard(img, w, h, c, flags, reps)
+            enc.encode_discard(img, w, h, c, flags, 1)
         else:
-            for _ in range(reps):
-                enc.encode(img, w, h, c, flags)
+            enc.encode(img, w, h, c, flags)
 
-    vals = []
-    with ThreadPoolExecutor(max_workers=cores) as ex:
-        for _ in range(steps):
-            t0 = time.perf_counter()
-            list(ex.map(work, range(cores)))
-            dt = time.perf_counter() - t0
-            vals.append(cores * reps * w * h / MP / dt)
-    sample = f"{cores} threads x {reps} encodes of the first {len(imgs)} workload images ({kind}) per step, ~{seconds:.0f}s"
+    vals, total = [], 0
+    for _ in range(steps):
+        calls, dt = _timed_pool(once, cores, seconds)
+        total += calls
+        vals.append(calls * w * h / MP / dt)
+    sample = f"{cores} threads, whole-image encodes of the first {len(imgs)} workload images ({kind}) for {seconds:.1f}s per step ({total} encodes)"
     return vals, cores, sample, ("reference" if use_ref else "port")
+
+
+def cpu_reference_decode_run(wl, kind: str, seconds: float):
+    """Reference decoder (fpng_decode_memory) on all usable host threads over reference-written files of the workload sample."""
+    from oracle.pyoracle import Oracle, Ref
+
+    cores = host_cores()
+    w, h, c, flags = wl["w"], wl["h"], wl["chans"], wl["flags"]
+    use_ref = Ref.available()
+    dec = Ref() if use_ref else Oracle()
+    files = [dec.encode(workload_image(wl, kind, i), w, h, c, flags) for i in range(min(cores, 8, wl["images"]))]
+
+    def once(k):
+        f = files[k % len(files)]
+        if use_ref:
+            dec.decode_discard(f, c, 1)
+        else:
+            dec.decode(f, c)
+
+    calls, dt = _timed_pool(once, cores, seconds)
+    return calls * w * h / MP / dt, cores, f"{cores} threads, {calls} decodes of {len(files)} reference-written workload files in {seconds:.1f}s", \
+        ("reference" if use_ref else "port")
 
 
 def run_reference(args, wl):
@@ -177,7 +231,7 @@ def run_reference(args, wl):
     if rank != 0:
         return 0
     total = max(args.steps + args.warmup, 1)
-    per_step = max(1.0, min(8.0, 60.0 / total))
+    per_step = max(0.5, min(8.0, 60.0 / total))
     vals, cores, sample, kind = cpu_reference_run(wl, args.kind, per_step, steps=args.warmup + args.steps)
     timed = vals[args.warmup:] or vals
     v = float(statistics.mean(timed))
@@ -227,6 +281,8 @@ def run_ours(args, wl):
     def step():
         fpng_b200.encode_batch_device(batch, flags, out=out, sizes=sizes, stream=stream.cuda_stream)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize(dev)
@@ -239,22 +295,22 @@ def run_ours(args, wl):
         from oracle.pyoracle import Oracle
         parity = got0 == Oracle().encode(workload_image(wl, args.kind, 0), w, h, c, flags)
 
-    sampler = ClockSampler(local)
     L.fpngb_profile_enable(1)
     launches0 = fpng_b200.launch_count()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize(dev)
+    wall1 = time.time()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, wall1)
     launches = fpng_b200.launch_count() - launches0
     ms = e0.elapsed_time(e1)
     prof = (C.c_float * 7)()
@@ -293,6 +349,61 @@ def run_ours(args, wl):
                        "frac_of_peak": (in_bytes + out_bytes) / 1e9 / (ms / args.steps / 1e3) / peak},
     }
 
+    # ---- decode leg: the rank's own encoded files, device resident (container walk on the host, outside the timed region)
+    if not args.no_decode:
+        sz_host = (sizes.cpu().numpy().astype(np.int64) & 0xFFFFFFFF)
+        files = [bytes(out[i, : int(sz_host[i])].cpu().numpy()) for i in range(n)]
+        files_dev, fstride, fsizes, fofs, flens, ww, hh, cc = fpng_b200.pack_files_for_device(files, dev)
+        px = torch.empty((n, h, w, c), dtype=torch.uint8, device=dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
+
+        def dstep():
+            fpng_b200.decode_batch_device(files_dev, fsizes, fofs, flens, w, h, c, c, out=px, status=status, stream=stream.cuda_stream)
+
+        for _ in range(3):
+            dstep()
+        torch.cuda.synchronize(dev)
+        dec_ok = bool((status == 0).all().item()) and bool(torch.equal(px, batch))
+        dsteps = max(1, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(stream)
+        for _ in range(dsteps):
+            dstep()
+        d1.record(stream)
+        torch.cuda.synchronize(dev)
+        td = torch.tensor([d0.elapsed_time(d1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dms = float(td.item()) / dsteps
+        dec_bytes = out_bytes + n * w * h * c
+        line["decode"] = {"value": world * n * w * h / MP / (dms / 1e3), "unit": "MP/s", "ms_per_step": dms, "steps": dsteps,
+                          "pixels_match_input": dec_ok, "algorithmic_gbs": dec_bytes / 1e9 / (dms / 1e3),
+                          "frac_of_peak": dec_bytes / 1e9 / (dms / 1e3) / peak,
+                          "input": "this rank's GPU-encoded files (byte-identical to reference-written files), device resident"}
+        del files_dev, px
+
+    # ---- the one NCCL gather of the encoded buffers (north_star), timed separately from the per-rank encode
+    if world > 1:
+        from fpng_b200.dist import gather_encoded
+        gather_encoded(out, sizes, 0)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        res = gather_encoded(out, sizes, 0)
+        g1.record(stream)
+        torch.cuda.synchronize(dev)
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        tb = torch.tensor([float(out_bytes)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb)
+        line["gather"] = {"ms": float(tg.item()), "bytes_total": float(tb.item()), "to_rank": 0,
+                          "gbs_into_rank0": (float(tb.item()) - out_bytes) / 1e9 / (float(tg.item()) / 1e3) if rank == 0 else None,
+                          "what": "all_gather(sizes) + compact kernel + grouped send/recv of every rank's encoded shard to rank 0 over NCCL"}
+        del res
+
     # ---- end to end through the C ABI with host (pinned) buffers: H2D + kernels + D2H inside the timed region
     n_e2e = min(n, args.e2e_images) if args.e2e_images else n
     hin = torch.empty((n_e2e, h, w, c), dtype=torch.uint8).pin_memory()
@@ -327,6 +438,9 @@ def run_ours(args, wl):
     if rank == 0 and world == 1 and not args.no_cpu:
         vals, cores, sample, kind = cpu_reference_run(wl, args.kind, args.cpu_seconds)
         line["cpu_baseline"] = {"value": float(vals[0]), "unit": "MP/s", "cores": cores, "kind": kind, "sample": sample}
+        if "decode" in line:
+            dv, dcores, dsample, dkind = cpu_reference_decode_run(wl, args.kind, max(2.0, args.cpu_seconds / 3))
+            line["decode"]["cpu_baseline"] = {"value": float(dv), "unit": "MP/s", "cores": dcores, "kind": dkind, "sample": dsample}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -346,6 +460,7 @@ def main():
     ap.add_argument("--e2e-images", type=int, default=0, help="images per e2e step (0 = the whole per-GPU batch)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

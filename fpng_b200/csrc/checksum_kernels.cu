@@ -240,3 +240,55 @@ uint32_t crc_ctas_for(size_t max_file_bytes)
 }
 
 }  // namespace fpngb
+
+// ------------------------------------------------------------------------------------------------
+// Compaction of a batch of encoded files (fixed stride, variable size) into one contiguous device buffer, each file
+// starting 16-byte aligned: the staging step before the NCCL gather of a rank's shard (fpng_b200/dist.py).
+// ------------------------------------------------------------------------------------------------
+namespace fpngb {
+
+__global__ void __launch_bounds__(1024) compact_offsets_kernel(const uint32_t* __restrict__ sizes, uint32_t n, unsigned long long* __restrict__ offsets)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+        const uint32_t i = i0 + tid;
+        const unsigned long long v = i < n ? (((unsigned long long)sizes[i] + 15ull) & ~15ull) : 0ull;
+        unsigned long long s = v;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, s, o); if (lane >= (uint32_t)o) s += u; }
+        if (lane == 31) s_warp[warp] = s;
+        __syncthreads();
+        unsigned long long wb = 0, tot = 0;
+        for (uint32_t k = 0; k < blockDim.x / 32; k++) { if (k < warp) wb += s_warp[k]; tot += s_warp[k]; }
+        if (i < n) offsets[i] = s_base + wb + s - v;
+        __syncthreads();
+        if (tid == 0) s_base += tot;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = s_base;
+}
+
+__global__ void __launch_bounds__(256) compact_copy_kernel(const uint8_t* __restrict__ files, size_t stride, const uint32_t* __restrict__ sizes,
+                                                            const unsigned long long* __restrict__ offsets, uint8_t* __restrict__ dst, size_t dst_cap)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t nvec = (sizes[f] + 15u) / 16u;
+    const unsigned long long o = offsets[f];
+    if (o + (unsigned long long)nvec * 16ull > dst_cap) return;
+    const uint4* src = reinterpret_cast<const uint4*>(files + (size_t)f * stride);
+    uint4* d = reinterpret_cast<uint4*>(dst + o);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) d[i] = src[i];
+}
+
+void launch_compact(const uint8_t* files, size_t stride, const uint32_t* sizes, uint32_t n, uint8_t* dst, size_t dst_cap,
+                    unsigned long long* offsets, cudaStream_t s)
+{
+    compact_offsets_kernel<<<1, 1024, 0, s>>>(sizes, n, offsets);
+    dim3 grid(64, n);
+    compact_copy_kernel<<<grid, 256, 0, s>>>(files, stride, sizes, offsets, dst, dst_cap);
+}
+
+}  // namespace fpngb

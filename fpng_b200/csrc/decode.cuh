@@ -4,8 +4,18 @@
 
 namespace fpngb {
 
-constexpr int kDecThreads = 512;            // subsequences decoded concurrently per file (one CTA per file)
-constexpr uint32_t kSubBits = 512;          // bits per subsequence (>> longest token: 12 + 5 + 1 bits)
+constexpr int kDecThreads = 256;            // subsequences per CTA in the scan / write kernels
+constexpr int kLinkThreads = 1024;          // subsequences linked per step by the per-file chain kernel
+constexpr uint32_t kSubBits = 1024;         // bits per subsequence (>> longest token: 12 + 5 + 1 bits)
+constexpr uint32_t kPreRoll = 256;          // speculative lead-in before a subsequence (self-synchronisation distance)
+
+// Per-subsequence record.  After decode_scan_kernel: start/exit/eob_end are absolute aligned-stream bit positions,
+// n_out/nlit/lits describe the tokens starting in the subsequence.  decode_link_kernel rewrites it for the write
+// kernel: exit := output byte offset, lits := the 4 literals preceding the subsequence, nlit := live flag.
+struct SubInfo {
+    unsigned long long start, exit, eob_end;
+    uint32_t n_out, lits, nlit, pad_;
+};
 
 struct FileDesc {                           // filled by the host container walk (fpng.cpp:2930-3077)
     uint32_t file_size, idat_ofs, idat_len, pad_;
@@ -23,7 +33,8 @@ struct DecodeParams {
     const uint8_t* d_files; size_t file_stride;
     const FileDesc* files;                  // [n] device
     DecodeState* state;                     // [n]
-    uint16_t* luts;                         // [n][4096]  sym | len << 9
+    uint32_t* luts;                         // [n][4096]  fused entries, see decode_kernels.cu
+    SubInfo* subs; uint32_t subs_per_file;  // [n][subs_per_file]
     uint8_t* delta; uint32_t delta_pitch;   // [n][h][pitch] filtered rows without the filter byte
     uint8_t* d_out; size_t out_stride;
     uint32_t* d_status;                     // [n] FPNG_DECODE_* codes

@@ -111,12 +111,13 @@ __global__ void __launch_bounds__(32) decode_prepare_kernel(DecodeParams p)
     __shared__ uint16_t s_cllut[128];
     __shared__ uint32_t s_next[17];
     __shared__ uint32_t s_fail;
+    __shared__ uint16_t s_base[4096];
     const uint32_t f = blockIdx.x, lane = threadIdx.x;
     const FileDesc fd = p.files[f];
     DecodeState* st = p.state + f;
     const uint8_t* z = p.d_files + (size_t)f * p.file_stride + fd.idat_ofs + 8;
     BitSrc src{z, fd.file_size - (fd.idat_ofs + 8)};
-    uint16_t* lut = p.luts + (size_t)f * 4096;
+    uint32_t* lut = p.luts + (size_t)f * 4096;
 
     if (lane == 0) {
         s_fail = 0;
@@ -175,137 +176,330 @@ __global__ void __launch_bounds__(32) decode_prepare_kernel(DecodeParams p)
     }
     __syncwarp();
     if (s_fail) { if (lane == 0) st->status = 1; return; }
-    if (!build_lut_warp(s_sizes, 288, lut, 12, lane, s_next)) { if (lane == 0) st->status = 1; }
+    if (!build_lut_warp(s_sizes, 288, s_base, 12, lane, s_next)) { if (lane == 0) st->status = 1; return; }
+    // Fuse a second literal into the entry when both codes fit in the 12 index bits (the reference augments its table the
+    // same way, fpng.cpp:2079-2102):  sym0 | len0 << 9 | sym1 << 13 | len1 << 21.
+    for (uint32_t i = lane; i < 4096; i += 32) {
+        const uint32_t e0 = s_base[i], sym0 = e0 & 511u, len0 = e0 >> 9;
+        uint32_t e = sym0 | (len0 << 9);
+        if (len0 && sym0 < 256u) {
+            const uint32_t e1 = s_base[i >> len0], sym1 = e1 & 511u, len1 = e1 >> 9;
+            if (len1 && sym1 < 256u && len0 + len1 <= 12u) e |= (sym1 << 13) | (len1 << 21);
+        }
+        lut[i] = e;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// D2: token decode
+// D2: token decode.  The token bit-string of a file is cut into subsequences of kSubBits bits (absolute multiples of
+// kSubBits in the aligned-stream bit coordinate).  Three kernels:
+//   D2a decode_scan_kernel   one thread per subsequence, all files and subsequences in parallel: the thread starts
+//                            kPreRoll bits early (speculatively), lets the self-synchronising prefix code lock on, takes
+//                            the first token boundary inside its subsequence as its start, then decodes to its exit (first
+//                            boundary in the next subsequence) counting output bytes and remembering the last 4 literals.
+//   D2b decode_link_kernel   one CTA per file walks the subsequences in order, 1024 at a time: verifies that every
+//                            subsequence starts where its predecessor exits (the first one starts exactly, so a verified
+//                            chain is the true parse), repairs the rare mismatches by re-decoding, and scans the byte
+//                            counts / literal windows into the output offset and "previous pixel" of every subsequence.
+//   D2c decode_write_kernel  one thread per live subsequence decodes again and writes the delta bytes.
 // ------------------------------------------------------------------------------------------------
-constexpr unsigned long long kPosEnd = ~0ull;            // subsequence saw the end-of-block code
-constexpr unsigned long long kPosErr = ~0ull - 1;        // subsequence hit an invalid code
+constexpr uint32_t kRelEnd = 0xFFFFFFFFu;              // exit flag (relative positions): saw the end-of-block code
+constexpr uint32_t kRelErr = 0xFFFFFFFEu;              // exit flag: invalid code
+constexpr unsigned long long kPosEnd = ~0ull;          // same flags in absolute (64-bit) form
+constexpr unsigned long long kPosErr = ~0ull - 1;
 
-struct SubResult {
-    unsigned long long exit;     // first token boundary at/after the subsequence end, or kPosEnd / kPosErr
-    unsigned long long eob_end;  // bit position right after the EOB code (valid when exit == kPosEnd)
-    uint32_t n_out;              // filtered-stream bytes produced by tokens that start inside the subsequence
-    uint32_t nlit;               // min(literal bytes produced, 4)
-    uint32_t lits;               // the last <= 4 literal bytes, most recent in the top byte
+// Aligned view of one file's zlib stream: 32-bit words starting at the 4-byte boundary at or before the stream.
+struct Stream {
+    const uint32_t* words;     // aligned base
+    uint32_t max_widx;         // last readable word index (reads beyond are clamped: garbage but in bounds)
+    uint32_t bit0;             // aligned-stream bit position of zlib bit 0 (0, 8, 16 or 24)
 };
 
-// Decode tokens from `start` while the token's first bit is below `end`.  kWrite = false: bookkeeping only.
-template <bool kWrite>
-__device__ __forceinline__ SubResult decode_subsequence(const BitSrc& src, const uint16_t* __restrict__ s_lut, unsigned long long start,
-                                                        unsigned long long end, uint32_t chans,
-                                                        // write mode:
-                                                        uint8_t* __restrict__ delta, uint32_t pitch, uint32_t bpl, uint32_t h,
-                                                        unsigned long long out_pos, uint32_t tail, uint32_t* err)
+__device__ __forceinline__ Stream open_stream(const uint8_t* file, const FileDesc& fd)
 {
-    SubResult r; r.exit = start; r.eob_end = 0; r.n_out = 0; r.nlit = 0; r.lits = 0;
-    if (start >= end) return r;                       // also covers kPosEnd / kPosErr pass-through
-    BitCursor bc; bc.seek(src, start);
-    uint32_t row = 0, col = 0;                        // position in the filtered stream (col 0 = filter byte)
-    uint32_t lits = tail;                             // write mode: rolling window of the last 4 literal bytes
-    if (kWrite) { row = (uint32_t)(out_pos / (bpl + 1ull)); col = (uint32_t)(out_pos % (bpl + 1ull)); }
-    while (bc.pos < end) {
-        bc.refill(src);
-        const uint32_t e = s_lut[bc.peek(12)], l = e >> 9, s = e & 511;
-        if (!l) { r.exit = kPosErr; return r; }
-        bc.skip(l);
-        if (s < 256) {
-            r.n_out++;
-            if (!kWrite) { r.lits = (r.lits >> 8) | (s << 24); r.nlit = min(r.nlit + 1u, 4u); }
-            else {
-                if (row >= h) { *err = 1; }
-                else if (col == 0) { if (s != (row ? 2u : 0u)) *err = 1; }          // fpng.cpp:2264, 2642
-                else delta[(size_t)row * pitch + (col - 1)] = (uint8_t)s;
+    Stream st;
+    const uint32_t zofs = fd.idat_ofs + 8;
+    st.words = reinterpret_cast<const uint32_t*>(file + (zofs & ~3u));
+    st.bit0 = (zofs & 3u) * 8u;
+    st.max_widx = ((fd.file_size + 3u) >> 2) - 1u - (zofs >> 2);     // file buffers are padded to a multiple of 4
+    return st;
+}
+
+struct Cursor {
+    unsigned long long buf; uint32_t cnt, widx;
+    __device__ __forceinline__ void seek(const Stream& st, unsigned long long abs_bit)
+    {
+        widx = (uint32_t)(abs_bit >> 5);
+        const uint32_t sh = (uint32_t)abs_bit & 31u;
+        const uint32_t lo = __ldg(st.words + min(widx, st.max_widx)), hi = __ldg(st.words + min(widx + 1u, st.max_widx));
+        buf = (((unsigned long long)hi << 32) | lo) >> sh;
+        cnt = 64u - sh; widx += 2u;
+    }
+    __device__ __forceinline__ void refill(const Stream& st)
+    {
+        if (cnt <= 32u) { buf |= (unsigned long long)__ldg(st.words + min(widx, st.max_widx)) << cnt; cnt += 32u; widx++; }
+    }
+    __device__ __forceinline__ void skip(uint32_t n) { buf >>= n; cnt -= n; }
+};
+
+struct SubScan {
+    uint32_t first;      // rel. position of the first token boundary >= lo (the subsequence's start)
+    uint32_t exit;       // rel. position of the first token boundary >= hi, or kRelEnd / kRelErr
+    uint32_t eob_end;    // rel. position right after the EOB code (exit == kRelEnd)
+    uint32_t n_out;      // bytes produced by tokens starting in [first, hi)
+    uint32_t nlit;       // literal bytes among them (saturating at 255)
+    uint32_t lits;       // last <= 4 literal bytes, most recent in the top byte
+};
+
+// Fused LUT entry: sym0 (9 bits) | len0 << 9 (4 bits) | sym1 << 13 (8 bits) | len1 << 21 (4 bits; 0 = no second literal)
+__device__ __forceinline__ uint32_t lut_sym0(uint32_t e) { return e & 511u; }
+__device__ __forceinline__ uint32_t lut_len0(uint32_t e) { return (e >> 9) & 15u; }
+__device__ __forceinline__ uint32_t lut_sym1(uint32_t e) { return (e >> 13) & 255u; }
+__device__ __forceinline__ uint32_t lut_len1(uint32_t e) { return e >> 21; }
+
+// Write side of the token decoder: consecutive delta bytes of a row are combined into aligned 32-bit stores (the words
+// a subsequence shares with its neighbours at either end, and row tails, go out as single bytes).
+struct DeltaSink {
+    uint8_t* delta; uint32_t pitch, bpl, h;
+    uint32_t row, col;            // position in the filtered stream; col 0 is the filter byte
+    uint8_t* ptr;                 // address of the next data byte of the current row
+    uint32_t acc, nacc;           // nacc pending bytes for the aligned word ending just before ptr
+    __device__ __forceinline__ void init(uint8_t* d, uint32_t pitch_, uint32_t bpl_, uint32_t h_, unsigned long long out_pos)
+    {
+        delta = d; pitch = pitch_; bpl = bpl_; h = h_;
+        row = (uint32_t)(out_pos / (bpl + 1ull)); col = (uint32_t)(out_pos % (bpl + 1ull));
+        ptr = delta + (size_t)row * pitch + (col ? col - 1u : 0u);
+        acc = 0; nacc = 0;
+    }
+    __device__ __forceinline__ void flush()
+    {
+        for (uint32_t i = 0; i < nacc; i++) ptr[(int)i - (int)nacc] = (uint8_t)(acc >> (8u * i));
+        nacc = 0; acc = 0;
+    }
+    __device__ __forceinline__ void next_row() { flush(); col = 0; row++; ptr = delta + (size_t)row * pitch; }
+    // one data byte (col >= 1, row < h)
+    __device__ __forceinline__ void put(uint32_t v)
+    {
+        if (nacc == 0 && ((uintptr_t)ptr & 3u)) { *ptr++ = (uint8_t)v; }
+        else {
+            acc |= v << (8u * nacc); nacc++; ptr++;
+            if (nacc == 4u) { *reinterpret_cast<uint32_t*>(ptr - 4) = acc; acc = 0; nacc = 0; }
+        }
+        if (++col > bpl) next_row();
+    }
+};
+
+// Decode from rel. position `rel` (origin = abs_origin bits in the aligned stream).  Tokens starting before `lo` are
+// pre-roll (not counted); tokens starting in [lo, hi) are counted / written.  kWrite writes delta bytes.
+template <bool kWrite>
+__device__ __forceinline__ SubScan decode_range(const Stream& st, const uint32_t* __restrict__ s_lut, unsigned long long abs_origin,
+                                                uint32_t rel, uint32_t lo, uint32_t hi, uint32_t chans,
+                                                uint8_t* __restrict__ delta, uint32_t pitch, uint32_t bpl, uint32_t h,
+                                                unsigned long long out_pos, uint32_t tail, uint32_t* err)
+{
+    SubScan r; r.first = lo; r.exit = 0; r.eob_end = 0; r.n_out = 0; r.nlit = 0; r.lits = 0;
+    Cursor c; c.seek(st, abs_origin + rel);
+    // ---- pre-roll: lock on to the token grid (speculative; an end-of-block or invalid code here means "not locked")
+    while (rel < lo) {
+        c.refill(st);
+        const uint32_t e = s_lut[(uint32_t)c.buf & 4095u];
+        uint32_t l = lut_len0(e);
+        const uint32_t s = lut_sym0(e);
+        if (!l || s == 256u || s > 285u) { rel = lo; c.seek(st, abs_origin + rel); break; }
+        if (s > 256u) { const uint32_t xb = c_len_xbits[s - 257u]; l += xb + 1u; }
+        c.skip(l); rel += l;
+    }
+    r.first = rel;
+    uint32_t lits = tail;
+    DeltaSink sink;
+    if (kWrite) sink.init(delta, pitch, bpl, h, out_pos);
+    uint32_t n_out = 0, nlit = 0;
+    while (rel < hi) {
+        c.refill(st);
+        const uint32_t e = s_lut[(uint32_t)c.buf & 4095u];
+        const uint32_t l0 = lut_len0(e), s = lut_sym0(e);
+        if (!l0) { r.exit = kRelErr; r.n_out = n_out; r.nlit = nlit; r.lits = lits; return r; }
+        if (s < 256u) {
+            // one literal, or two when the fused second literal also starts inside the subsequence
+            const uint32_t l1 = lut_len1(e);
+            const bool two = l1 && (rel + l0 < hi);
+            const uint32_t l = two ? l0 + l1 : l0;
+            c.skip(l); rel += l;
+            const uint32_t cntl = two ? 2u : 1u;
+            n_out += cntl; nlit += cntl;
+            if (!kWrite) {
                 lits = (lits >> 8) | (s << 24);
-                if (++col > bpl) { col = 0; row++; }
+                if (two) lits = (lits >> 8) | (lut_sym1(e) << 24);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    if (k == 1 && !two) break;
+                    const uint32_t v = k ? lut_sym1(e) : s;
+                    lits = (lits >> 8) | (v << 24);
+                    if (sink.row >= h) *err = 1;
+                    else if (sink.col == 0) { if (v != (sink.row ? 2u : 0u)) *err = 1; sink.col = 1; }   // fpng.cpp:2264, 2642
+                    else sink.put(v);
+                }
             }
-        } else if (s == 256) {
-            r.exit = kPosEnd; r.eob_end = bc.pos;
+        } else if (s == 256u) {
+            c.skip(l0); rel += l0;
+            if (kWrite) sink.flush();
+            r.exit = kRelEnd; r.eob_end = rel; r.n_out = n_out; r.nlit = nlit; r.lits = lits;
             return r;
         } else {
-            if (s > 285) { r.exit = kPosErr; return r; }
-            const uint32_t xb = c_len_xbits[s - 257];
-            const uint32_t run = c_len_base[s - 257] + bc.peek(xb);
-            bc.skip(xb + 1);                                                      // extra bits + the 1-bit distance code (fpng.cpp:2300)
-            r.n_out += run;
+            if (s > 285u) { r.exit = kRelErr; r.n_out = n_out; r.nlit = nlit; r.lits = lits; return r; }
+            c.skip(l0);
+            const uint32_t xb = c_len_xbits[s - 257u];
+            const uint32_t run = c_len_base[s - 257u] + ((uint32_t)c.buf & ((1u << xb) - 1u));
+            c.skip(xb + 1u);                                                       // extra bits + the 1-bit distance code (fpng.cpp:2300)
+            rel += l0 + xb + 1u;
+            n_out += run;
             if (kWrite) {
-                // run of the previous delta pixel: must start on a pixel boundary after at least one pixel of the row,
-                // be a whole number of pixels and stay inside the row (fpng.cpp:2302-2315, 2681-2691, 2727)
-                const bool bad = row >= h || col < 1 + chans || ((col - 1) % chans) != 0 || (run % chans) != 0 || (col - 1) + run > bpl;
-                if (bad) { *err = 1; col += run; while (col > bpl) { col -= bpl + 1; row++; } }
-                else {
-                    uint8_t* d = delta + (size_t)row * pitch + (col - 1);
-                    const uint32_t px = chans == 4 ? lits : (lits >> 8);          // last `chans` literals, oldest in the low byte
-                    if (chans == 4) for (uint32_t i = 0; i < run; i += 4) { d[i] = (uint8_t)px; d[i + 1] = (uint8_t)(px >> 8); d[i + 2] = (uint8_t)(px >> 16); d[i + 3] = (uint8_t)(px >> 24); }
-                    else for (uint32_t i = 0; i < run; i += 3) { d[i] = (uint8_t)px; d[i + 1] = (uint8_t)(px >> 8); d[i + 2] = (uint8_t)(px >> 16); }
-                    col += run;
-                    if (col > bpl) { col = 0; row++; }
+                // run of the previous delta pixel: starts on a pixel boundary after at least one pixel of the row, is a
+                // whole number of pixels and stays inside the row (fpng.cpp:2302-2315, 2681-2691, 2727)
+                const uint32_t row = sink.row, col = sink.col;
+                const bool bad = row >= h || col < 1u + chans || ((col - 1u) % chans) != 0 || (run % chans) != 0 || (col - 1u) + run > bpl;
+                if (bad) { *err = 1; return r; }
+                const uint32_t px = chans == 4 ? lits : (lits >> 8);              // last `chans` literals, oldest in the low byte
+                if (chans == 4) {
+                    // RGBA pixels are word aligned in the delta rows: one 32-bit store per pixel
+                    sink.flush();
+                    uint32_t* d = reinterpret_cast<uint32_t*>(sink.ptr);
+                    const uint32_t npx = run >> 2;
+                    for (uint32_t i = 0; i < npx; i++) d[i] = px;
+                    sink.ptr += run; sink.col += run;
+                    if (sink.col > bpl) sink.next_row();
+                } else {
+                    for (uint32_t i = 0; i < run; i += 3) { sink.put(px & 0xFFu); sink.put((px >> 8) & 0xFFu); sink.put(px >> 16); }
                 }
             }
         }
     }
-    r.exit = bc.pos;
+    if (kWrite) sink.flush();
+    r.exit = rel; r.n_out = n_out; r.nlit = nlit; r.lits = lits;
     return r;
 }
 
-// "keep the last 4 literal bytes" monoid: a then b
+// "keep the last 4 literal bytes" monoid: a then b  (v holds the last n literals, most recent in the top byte)
 __device__ __forceinline__ void lit_combine(uint32_t& n, uint32_t& v, uint32_t nb, uint32_t vb)
 {
-    // v holds the last n literals with the most recent in the top byte
-    if (nb >= 4) { n = 4; v = vb; return; }
-    if (nb == 0) return;
-    v = (v >> (8 * nb)) | vb;      // vb's valid bytes occupy its top nb bytes, low bytes are zero by construction
+    if (nb >= 4u) { n = 4u; v = vb; return; }
+    if (nb == 0u) return;
+    v = (v >> (8u * nb)) | (vb & (0xFFFFFFFFu << (8u * (4u - nb))));
     n = min(n + nb, 4u);
 }
 
-__global__ void __launch_bounds__(kDecThreads) decode_tokens_kernel(DecodeParams p)
+// subsequence g of a file covers aligned-stream bits [g*kSubBits, (g+1)*kSubBits)
+struct FileSpan { unsigned long long tok0; unsigned long long g0, g1; };     // first token bit; first/last subsequence index
+__device__ __forceinline__ FileSpan file_span(const DecodeState& st, const Stream& sm, const FileDesc& fd)
 {
-    __shared__ uint16_t s_lut[4096];
-    __shared__ unsigned long long s_exit[kDecThreads];
-    __shared__ unsigned long long s_scan[kDecThreads / 32];
-    __shared__ uint32_t s_litn[kDecThreads / 32], s_litv[kDecThreads / 32];
+    FileSpan f;
+    f.tok0 = st.token_start + sm.bit0;
+    const unsigned long long endbit = (unsigned long long)(fd.idat_len > 4u ? fd.idat_len - 4u : 0u) * 8ull + sm.bit0;   // tokens (and EOB) end before the Adler bytes
+    f.g0 = f.tok0 / kSubBits;
+    f.g1 = endbit ? (endbit - 1ull) / kSubBits : 0ull;
+    if (f.g1 < f.g0) f.g1 = f.g0;
+    return f;
+}
+
+__global__ void __launch_bounds__(kDecThreads) decode_scan_kernel(DecodeParams p)
+{
+    __shared__ uint32_t s_lut[4096];
+    const uint32_t f = blockIdx.y, tid = threadIdx.x;
+    const DecodeState st = p.state[f];
+    if (st.status || st.stored) return;
+    const FileDesc fd = p.files[f];
+    const Stream sm = open_stream(p.d_files + (size_t)f * p.file_stride, fd);
+    const FileSpan sp = file_span(st, sm, fd);
+    const unsigned long long g = sp.g0 + (unsigned long long)blockIdx.x * kDecThreads + tid;
+    if (sp.g0 + (unsigned long long)blockIdx.x * kDecThreads > sp.g1) return;
+    for (uint32_t i = tid; i < 4096; i += blockDim.x) s_lut[i] = p.luts[(size_t)f * 4096 + i];
+    __syncthreads();
+    if (g > sp.g1) return;
+    SubInfo* info = p.subs + (size_t)f * p.subs_per_file + (g - sp.g0);
+    const unsigned long long lo_abs = g * kSubBits;
+    SubScan r;
+    unsigned long long origin;
+    if (g == sp.g0) {            // the file's first subsequence starts exactly at the first token
+        origin = sp.tok0;
+        r = decode_range<false>(sm, s_lut, origin, 0u, 0u, (uint32_t)((g + 1) * kSubBits - origin), p.chans, nullptr, 0, 0, 0, 0, 0, nullptr);
+    } else {
+        origin = lo_abs - kPreRoll < sp.tok0 ? sp.tok0 : lo_abs - kPreRoll;     // never pre-roll across the block header
+        r = decode_range<false>(sm, s_lut, origin, 0u, (uint32_t)(lo_abs - origin), (uint32_t)(lo_abs - origin) + kSubBits, p.chans, nullptr, 0, 0, 0, 0, 0, nullptr);
+    }
+    info->start = origin + r.first;
+    info->exit = r.exit >= kRelErr ? (r.exit == kRelEnd ? kPosEnd : kPosErr) : origin + r.exit;
+    info->eob_end = origin + r.eob_end;
+    info->n_out = r.n_out; info->lits = r.lits; info->nlit = min(r.nlit, 4u);
+}
+
+__global__ void __launch_bounds__(kLinkThreads) decode_link_kernel(DecodeParams p)
+{
+    __shared__ uint32_t s_lut[4096];
+    __shared__ unsigned long long s_exit[kLinkThreads];
+    __shared__ unsigned long long s_scan[kLinkThreads / 32];
+    __shared__ uint32_t s_litn[kLinkThreads / 32], s_litv[kLinkThreads / 32];
     __shared__ unsigned long long s_carry_start, s_carry_out, s_eob_end;
-    __shared__ uint32_t s_carry_litn, s_carry_litv, s_done, s_err;
+    __shared__ uint32_t s_carry_litn, s_carry_litv, s_done, s_err, s_first_bad, s_lut_loaded;
 
     const uint32_t f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    DecodeState* st = p.state + f;
-    if (st->status || st->stored) return;
+    DecodeState* stp = p.state + f;
+    if (stp->status || stp->stored) return;
+    const DecodeState st = *stp;
     const FileDesc fd = p.files[f];
-    const uint8_t* z = p.d_files + (size_t)f * p.file_stride + fd.idat_ofs + 8;
-    BitSrc src{z, fd.file_size - (fd.idat_ofs + 8)};
-    const uint32_t chans = p.chans, bpl = p.w * chans, h = p.h, pitch = p.delta_pitch;
-    uint8_t* delta = p.delta + (size_t)f * pitch * h;
+    const Stream sm = open_stream(p.d_files + (size_t)f * p.file_stride, fd);
+    const FileSpan sp = file_span(st, sm, fd);
+    const uint32_t chans = p.chans, bpl = p.w * chans, h = p.h;
     const unsigned long long total_out = (unsigned long long)(bpl + 1) * h;
+    SubInfo* subs = p.subs + (size_t)f * p.subs_per_file;
+    const unsigned long long nsub = sp.g1 - sp.g0 + 1ull;
 
-    for (uint32_t i = tid; i < 4096; i += blockDim.x) s_lut[i] = p.luts[(size_t)f * 4096 + i];
-    if (tid == 0) { s_carry_start = st->token_start; s_carry_out = 0; s_carry_litn = 0; s_carry_litv = 0; s_done = 0; s_err = 0; s_eob_end = 0; }
+    if (tid == 0) { s_carry_start = sp.tok0; s_carry_out = 0; s_carry_litn = 0; s_carry_litv = 0; s_done = 0; s_err = 0; s_eob_end = 0; s_lut_loaded = 0; }
     __syncthreads();
 
-    const unsigned long long first_sub = s_carry_start / kSubBits;
-    for (unsigned long long chunk = 0; ; chunk++) {
-        const unsigned long long g = first_sub + chunk * kDecThreads + tid;       // absolute subsequence index
-        const unsigned long long end = (g + 1) * kSubBits;
-        unsigned long long start = tid == 0 ? s_carry_start : g * kSubBits;
-        SubResult r = decode_subsequence<false>(src, s_lut, start, end, chans, nullptr, 0, 0, 0, 0, 0, nullptr);
-        // iterate until every subsequence starts where its predecessor exits
-        for (;;) {
-            s_exit[tid] = r.exit;
+    for (unsigned long long base = 0; base < nsub; base += kLinkThreads) {
+        const unsigned long long i = base + tid;
+        const bool have = i < nsub;
+        SubInfo in;
+        if (have) in = subs[i];
+        else { in.start = 0; in.exit = kPosErr; in.eob_end = 0; in.n_out = 0; in.lits = 0; in.nlit = 0; }
+        const unsigned long long g = sp.g0 + i;
+        // ---- verify / repair the chain: every subsequence must start where its predecessor exits
+        for (uint32_t iter = 0;; iter++) {
+            s_exit[tid] = in.exit;
             __syncthreads();
             const unsigned long long want = tid == 0 ? s_carry_start : s_exit[tid - 1];
-            int changed = 0;
-            if (want != start) {
-                start = want;
-                if (want == kPosEnd || want == kPosErr) { r.exit = want; r.n_out = 0; r.nlit = 0; r.lits = 0; r.eob_end = 0; }
-                else r = decode_subsequence<false>(src, s_lut, start, end, chans, nullptr, 0, 0, 0, 0, 0, nullptr);
-                changed = 1;
+            const int mismatch = have && want < kPosErr && want != in.start;
+            if (!__syncthreads_or(mismatch)) break;
+            if (!s_lut_loaded) {                       // repairs are rare: fetch the LUT only when first needed
+                for (uint32_t k = tid; k < 4096; k += blockDim.x) s_lut[k] = p.luts[(size_t)f * 4096 + k];
+                __syncthreads();
+                if (tid == 0) s_lut_loaded = 1;
             }
-            if (!__syncthreads_or(changed)) break;
+            if (mismatch) {
+                const unsigned long long hi_abs = (g + 1) * kSubBits;
+                if (want >= hi_abs) { in.start = want; in.exit = want; in.n_out = 0; in.nlit = 0; in.lits = 0; }   // cannot happen for kSubBits >> token size
+                else {
+                    const SubScan r = decode_range<false>(sm, s_lut, want, 0u, 0u, (uint32_t)(hi_abs - want), chans, nullptr, 0, 0, 0, 0, 0, nullptr);
+                    in.start = want;
+                    in.exit = r.exit >= kRelErr ? (r.exit == kRelEnd ? kPosEnd : kPosErr) : want + r.exit;
+                    in.eob_end = want + r.eob_end; in.n_out = r.n_out; in.lits = r.lits; in.nlit = min(r.nlit, 4u);
+                }
+            }
+            __syncthreads();
         }
-        // block-exclusive scans: output byte offsets and the literal window entering each subsequence
-        unsigned long long incl = r.n_out;
-        uint32_t wn = r.nlit, wv = r.lits;
+        // the first subsequence that ends in EOB / an invalid code terminates the stream; everything after it is dead
+        if (tid == 0) s_first_bad = kLinkThreads;
+        __syncthreads();
+        if (in.exit >= kPosErr) atomicMin(&s_first_bad, tid);
+        __syncthreads();
+        const uint32_t first_bad = s_first_bad;
+        const bool live = have && tid <= first_bad;
+        if (!live) { in.n_out = 0; in.nlit = 0; in.lits = 0; }
+
+        // ---- block-exclusive scans: output byte offset and literal window entering each subsequence
+        unsigned long long incl = in.n_out;
+        uint32_t wn = in.nlit, wv = in.lits;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned long long up = __shfl_up_sync(kFullMask, incl, o);
@@ -313,47 +507,73 @@ __global__ void __launch_bounds__(kDecThreads) decode_tokens_kernel(DecodeParams
             if (lane >= (uint32_t)o) { incl += up; uint32_t tn = un, tv = uv; lit_combine(tn, tv, wn, wv); wn = tn; wv = tv; }
         }
         if (lane == 31) { s_scan[warp] = incl; s_litn[warp] = wn; s_litv[warp] = wv; }
-        // exclusive values inside the warp
         unsigned long long ex = __shfl_up_sync(kFullMask, incl, 1);
         uint32_t en = __shfl_up_sync(kFullMask, wn, 1), ev = __shfl_up_sync(kFullMask, wv, 1);
         if (lane == 0) { ex = 0; en = 0; ev = 0; }
         __syncthreads();
         unsigned long long wbase = 0, chunk_total = 0;
         uint32_t bn = s_carry_litn, bv = s_carry_litv, cn = bn, cv = bv;
-        for (uint32_t i = 0; i < kDecThreads / 32; i++) {
-            if (i < warp) { wbase += s_scan[i]; lit_combine(bn, bv, s_litn[i], s_litv[i]); }
-            chunk_total += s_scan[i];
-            lit_combine(cn, cv, s_litn[i], s_litv[i]);
+        for (uint32_t k = 0; k < kLinkThreads / 32; k++) {
+            if (k < warp) { wbase += s_scan[k]; lit_combine(bn, bv, s_litn[k], s_litv[k]); }
+            chunk_total += s_scan[k];
+            lit_combine(cn, cv, s_litn[k], s_litv[k]);
         }
-        lit_combine(bn, bv, en, ev);                                             // window entering this subsequence
+        lit_combine(bn, bv, en, ev);
         const unsigned long long out_pos = s_carry_out + wbase + ex;
 
-        // write pass
-        uint32_t err = 0;
-        if (r.exit == kPosErr) err = 1;
-        if (r.n_out || r.exit == kPosEnd) {
-            if (out_pos + r.n_out > total_out) err = 1;
-            else decode_subsequence<true>(src, s_lut, start, end, chans, delta, pitch, bpl, h, out_pos, bv, &err);
+        if (have) {
+            SubInfo o;
+            o.start = in.start; o.exit = out_pos; o.eob_end = 0; o.n_out = live ? in.n_out : 0u; o.lits = bv; o.nlit = live ? 1u : 0u;
+            if (live && out_pos + in.n_out > total_out) { o.n_out = 0; o.nlit = 0; s_err = 1; }
+            subs[i] = o;
         }
-        if (r.exit == kPosEnd && start != kPosEnd) { s_eob_end = r.eob_end; s_done = 1; }
-        if (err) s_err = 1;
+        if (have && tid == first_bad) { if (in.exit == kPosEnd) { s_eob_end = in.eob_end; s_done = 1; } else s_err = 1; }
         __syncthreads();
         if (tid == 0) {
-            s_carry_start = s_exit[kDecThreads - 1];
+            s_carry_start = s_exit[kLinkThreads - 1];
             s_carry_out += chunk_total; s_carry_litn = cn; s_carry_litv = cv;
-            if (s_carry_start == kPosErr) s_err = 1;
             if (s_carry_out > total_out) s_err = 1;
         }
         __syncthreads();
-        if (s_done || s_err) break;
+        if (s_done || s_err) {
+            // mark the remaining subsequences dead so the write kernel skips them
+            for (unsigned long long k = base + kLinkThreads + tid; k < nsub; k += kLinkThreads) { subs[k].n_out = 0; subs[k].nlit = 0; }
+            break;
+        }
     }
+    __syncthreads();
     if (tid == 0) {
         // EOB right after the last row, then pad to a byte, then exactly the 4 Adler bytes (fpng.cpp:2559-2584)
-        const unsigned long long used = (s_eob_end + 7) >> 3;
-        const bool ok = !s_err && s_done && s_carry_out == total_out && used + 4 == fd.idat_len;
-        st->status = ok ? 0u : 1u;
-        st->out_bytes = s_carry_out; st->end_byte = used;
+        const unsigned long long used = s_eob_end >= sm.bit0 ? ((s_eob_end - sm.bit0 + 7ull) >> 3) : 0ull;
+        const bool ok = !s_err && s_done && s_carry_out == total_out && used + 4ull == fd.idat_len;
+        stp->status = ok ? 0u : 1u;
+        stp->out_bytes = s_carry_out; stp->end_byte = used;
     }
+}
+
+__global__ void __launch_bounds__(kDecThreads) decode_write_kernel(DecodeParams p)
+{
+    __shared__ uint32_t s_lut[4096];
+    const uint32_t f = blockIdx.y, tid = threadIdx.x;
+    DecodeState* stp = p.state + f;
+    if (stp->status || stp->stored) return;
+    const FileDesc fd = p.files[f];
+    const Stream sm = open_stream(p.d_files + (size_t)f * p.file_stride, fd);
+    const FileSpan sp = file_span(*stp, sm, fd);
+    if (sp.g0 + (unsigned long long)blockIdx.x * kDecThreads > sp.g1) return;
+    for (uint32_t i = tid; i < 4096; i += blockDim.x) s_lut[i] = p.luts[(size_t)f * 4096 + i];
+    __syncthreads();
+    const unsigned long long g = sp.g0 + (unsigned long long)blockIdx.x * kDecThreads + tid;
+    if (g > sp.g1) return;
+    const SubInfo in = p.subs[(size_t)f * p.subs_per_file + (g - sp.g0)];
+    if (!in.nlit || !in.n_out) return;                                           // dead or empty
+    const uint32_t chans = p.chans, bpl = p.w * chans, h = p.h, pitch = p.delta_pitch;
+    uint32_t err = 0;
+    const unsigned long long hi_abs = (g + 1) * kSubBits;
+    if (in.start < hi_abs)
+        decode_range<true>(sm, s_lut, in.start, 0u, 0u, (uint32_t)(hi_abs - in.start), chans, p.delta + (size_t)f * pitch * h, pitch, bpl, h,
+                           in.exit /*out_pos*/, in.lits /*tail*/, &err);
+    if (err) stp->status = 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -426,40 +646,50 @@ __global__ void __launch_bounds__(128) unfilter_kernel(DecodeParams p)
 #pragma unroll
     for (int i = 0; i < SRC; i++) acc[i] = 0;
     const bool summing = !st.stored;
-    for (uint32_t y = 0; y < h; y++) {
-        uint32_t d[SRC];
-        const uint8_t* dr = delta + (size_t)y * pitch;
-        if (full) {
+    constexpr int kRowsAhead = 4;                  // independent loads in flight per thread
+    for (uint32_t y0 = 0; y0 < h; y0 += kRowsAhead) {
+        uint32_t dd[kRowsAhead][SRC];
 #pragma unroll
-            for (int i = 0; i < SRC; i++) d[i] = *reinterpret_cast<const uint32_t*>(dr + 4 * i);   // pitch % 16 == 0 and x0*SRC % 4 == 0
-        } else {
+        for (int j = 0; j < kRowsAhead; j++) {
+            const uint32_t y = min(y0 + j, h - 1);
+            const uint8_t* dr = delta + (size_t)y * pitch;
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < SRC; i++) { d[i] = 0; for (int b = 0; b < 4; b++) if ((uint32_t)(4 * i + b) < npx * SRC) d[i] |= (uint32_t)dr[4 * i + b] << (8 * b); }
+                for (int i = 0; i < SRC; i++) dd[j][i] = __ldg(reinterpret_cast<const uint32_t*>(dr + 4 * i));   // pitch % 16 == 0 and x0*SRC % 4 == 0
+            } else {
+#pragma unroll
+                for (int i = 0; i < SRC; i++) { dd[j][i] = 0; for (int b = 0; b < 4; b++) if ((uint32_t)(4 * i + b) < npx * SRC) dd[j][i] |= (uint32_t)dr[4 * i + b] << (8 * b); }
+            }
         }
 #pragma unroll
-        for (int i = 0; i < SRC; i++) acc[i] = summing ? vadd4(acc[i], d[i]) : d[i];
-        // repack to DST channels
-        uint32_t o[DST];
-        if (SRC == DST) {
+        for (int j = 0; j < kRowsAhead; j++) {
+            const uint32_t y = y0 + j;
+            if (y >= h) break;
 #pragma unroll
-            for (int i = 0; i < DST; i++) o[i] = acc[i];
-        } else if (SRC == 3) {   // 24 -> 32 bpp, alpha 0xFF (fpng.cpp:2331)
-            o[0] = (acc[0] & 0x00FFFFFFu) | 0xFF000000u;
-            o[1] = __byte_perm(acc[0], acc[1], 0x4543) | 0xFF000000u;
-            o[2] = __byte_perm(acc[1], acc[2], 0x4432) | 0xFF000000u;
-            o[DST - 1] = (acc[2] >> 8) | 0xFF000000u;
-        } else {                 // 32 -> 24 bpp, alpha dropped (fpng.cpp:2684-2721)
-            o[0] = __byte_perm(acc[0], acc[1], 0x4210);
-            o[1] = __byte_perm(acc[1], acc[2], 0x5421);
-            o[DST - 1] = __byte_perm(acc[2], acc[SRC - 1], 0x6542);
-        }
-        uint8_t* orow = out + (size_t)y * out_pitch;
-        if (full && out_aligned) {
+            for (int i = 0; i < SRC; i++) acc[i] = summing ? vadd4(acc[i], dd[j][i]) : dd[j][i];
+            // repack to DST channels
+            uint32_t o[DST];
+            if (SRC == DST) {
 #pragma unroll
-            for (int i = 0; i < DST; i++) *reinterpret_cast<uint32_t*>(orow + 4 * i) = o[i];
-        } else {
+                for (int i = 0; i < DST; i++) o[i] = acc[i];
+            } else if (SRC == 3) {   // 24 -> 32 bpp, alpha 0xFF (fpng.cpp:2331)
+                o[0] = (acc[0] & 0x00FFFFFFu) | 0xFF000000u;
+                o[1] = __byte_perm(acc[0], acc[1], 0x4543) | 0xFF000000u;
+                o[2] = __byte_perm(acc[1], acc[2], 0x4432) | 0xFF000000u;
+                o[DST - 1] = (acc[2] >> 8) | 0xFF000000u;
+            } else {                 // 32 -> 24 bpp, alpha dropped (fpng.cpp:2684-2721)
+                o[0] = __byte_perm(acc[0], acc[1], 0x4210);
+                o[1] = __byte_perm(acc[1], acc[2], 0x5421);
+                o[DST - 1] = __byte_perm(acc[2], acc[SRC - 1], 0x6542);
+            }
+            uint8_t* orow = out + (size_t)y * out_pitch;
+            if (full && out_aligned) {
 #pragma unroll
-            for (int i = 0; i < DST; i++) for (int b = 0; b < 4; b++) if ((uint32_t)(4 * i + b) < npx * DST) orow[4 * i + b] = (uint8_t)(o[i] >> (8 * b));
+                for (int i = 0; i < DST; i++) *reinterpret_cast<uint32_t*>(orow + 4 * i) = o[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < DST; i++) for (int b = 0; b < 4; b++) if ((uint32_t)(4 * i + b) < npx * DST) orow[4 * i + b] = (uint8_t)(o[i] >> (8 * b));
+            }
         }
     }
 }
@@ -473,7 +703,11 @@ __global__ void decode_status_kernel(DecodeParams p, uint32_t n)
 void launch_decode(const DecodeParams& p, uint32_t n, uint32_t desired, cudaStream_t s)
 {
     decode_prepare_kernel<<<n, 32, 0, s>>>(p);
-    decode_tokens_kernel<<<n, kDecThreads, 0, s>>>(p);
+    const uint32_t sub_blocks = (p.subs_per_file + kDecThreads - 1) / kDecThreads;
+    dim3 gsub(sub_blocks, n);
+    decode_scan_kernel<<<gsub, kDecThreads, 0, s>>>(p);
+    decode_link_kernel<<<n, kLinkThreads, 0, s>>>(p);
+    decode_write_kernel<<<gsub, kDecThreads, 0, s>>>(p);
     dim3 gs((p.h + 7) / 8, n);
     decode_stored_kernel<<<gs, 256, 0, s>>>(p);
     const uint32_t groups = (p.w + 3) / 4;

@@ -538,6 +538,19 @@ uint32_t fpngb_adler32(const void* data, size_t size, uint32_t adler)
     return (uint32_t)((B << 16) | A);
 }
 
+int fpngb_compact_batch_device(const void* d_files, size_t stride, const uint32_t* d_sizes, uint32_t n, void* d_dst, size_t dst_cap,
+                               uint64_t* d_offsets, void* stream)
+{
+    if (!g_ctx.ready) return FPNGB_ERR_NOT_INITIALIZED;
+    if (!d_files || !d_sizes || !d_dst || !d_offsets || n == 0 || n > 65535) return FPNGB_ERR_INVALID_ARG;
+    if (stride % 16 || (uintptr_t)d_files % 16 || (uintptr_t)d_dst % 16) return FPNGB_ERR_ALIGNMENT;
+    FPNGB_CUDA_OK(cudaSetDevice(g_ctx.device));
+    launch_compact((const uint8_t*)d_files, stride, d_sizes, n, (uint8_t*)d_dst, dst_cap, (unsigned long long*)d_offsets, (cudaStream_t)stream);
+    count_launch(2);
+    FPNGB_CUDA_OK(cudaGetLastError());
+    return FPNGB_OK;
+}
+
 void* fpngb_host_alloc(size_t bytes)
 {
     void* p = nullptr;

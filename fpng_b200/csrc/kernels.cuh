@@ -69,6 +69,8 @@ void launch_huffman_build(const HuffParams& p, uint32_t n, cudaStream_t s);
 uint32_t crc_ctas_for(size_t max_file_bytes);
 uint32_t adler_chunk_bytes();
 void launch_adler_buffer(const uint8_t* d_buf, size_t n, uint2* d_partials, cudaStream_t s);
+void launch_compact(const uint8_t* files, size_t stride, const uint32_t* sizes, uint32_t n, uint8_t* dst, size_t dst_cap,
+                    unsigned long long* offsets, cudaStream_t s);
 int  checksum_tables_init();                      // uploads CRC slice tables / x^(2^k) powers (idempotent)
 
 // host helpers shared by host_api.cu and the tests

@@ -106,6 +106,12 @@ FPNGB_API int fpngb_get_info_ex(const void* file, uint32_t size, uint32_t* w, ui
 FPNGB_API uint32_t fpngb_crc32(const void* data, size_t size, uint32_t prev_crc32);
 FPNGB_API uint32_t fpngb_adler32(const void* data, size_t size, uint32_t adler);
 
+/* Packs the n variable-size files of a batch (d_files + i*stride, d_sizes[i]) back to back into d_dst, each file
+ * starting 16-byte aligned; d_offsets receives n+1 byte offsets (offsets[n] = total).  New (no reference counterpart):
+ * the staging step before the single NCCL gather of a rank's encoded shard (BASELINE.json north_star). */
+FPNGB_API int fpngb_compact_batch_device(const void* d_files, size_t stride, const uint32_t* d_sizes, uint32_t n,
+                                         void* d_dst, size_t dst_cap, uint64_t* d_offsets, void* stream);
+
 /* Pinned host memory helpers for callers that want full PCIe bandwidth through the *_host entry points. */
 FPNGB_API void* fpngb_host_alloc(size_t bytes);
 FPNGB_API void fpngb_host_free(void* p);

@@ -143,6 +143,8 @@ class Ref:
         L.ref_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
         L.ref_encode_discard.restype = C.c_size_t
         L.ref_encode_discard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.ref_decode_discard.restype = C.c_int
+        L.ref_decode_discard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
         L.ref_get_info.restype = C.c_int
         L.ref_get_info.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, u32p]
         L.ref_decode.restype = C.c_int
@@ -178,6 +180,10 @@ class Ref:
     def encode_discard(self, img, w, h, chans, flags=0, reps=1) -> int:
         a = _as_u8(img)
         return self.L.ref_encode_discard(_ptr(a), w, h, chans, flags, reps)
+
+    def decode_discard(self, data, desired, reps=1) -> int:
+        a = _as_u8(data)
+        return self.L.ref_decode_discard(_ptr(a), a.size, desired, reps)
 
     def get_info(self, data):
         a = _as_u8(data)

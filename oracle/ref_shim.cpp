@@ -49,6 +49,18 @@ REF_API size_t ref_encode_discard(const void* img, uint32_t w, uint32_t h, uint3
     return s;
 }
 
+// Decode-only timing helper (decodes `reps` times, keeps the vector allocation inside the loop like fpng_test).
+REF_API int ref_decode_discard(const void* file, uint32_t size, uint32_t desired, int reps)
+{
+    int st = 0;
+    for (int i = 0; i < reps; i++) {
+        std::vector<uint8_t> buf; uint32_t w, h, c;
+        st = fpng::fpng_decode_memory(file, size, buf, w, h, c, desired);
+        if (st) return st;
+    }
+    return st;
+}
+
 REF_API int ref_get_info(const void* file, uint32_t size, uint32_t* w, uint32_t* h, uint32_t* chans)
 {
     return fpng::fpng_get_info(file, size, *w, *h, *chans);
