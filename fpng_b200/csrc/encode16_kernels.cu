@@ -1,0 +1,301 @@
+// fpng_b200/csrc/encode16_kernels.cu -- second-generation scan (K1) and pack (K3) kernels on the 16-pixels-per-lane
+// walker (row_walk16.cuh).  Same outputs, bit for bit, as the generic kernels in encode_kernels.cu; used whenever every
+// scanline is 16-byte aligned (all BASELINE.json shapes).  Reference lines: see encode_kernels.cu.
+#include "row_walk16.cuh"
+#include "kernels.cuh"
+
+namespace fpngb {
+
+constexpr int kScan16Rows = 8;                   // warps (scanlines) per CTA, scan
+constexpr int kPack16Rows = 4;                   // warps per CTA, pack (larger staging buffers)
+constexpr int kStage16Words = 1072;              // >= (31 + 12 + 512 * 66) / 32 + 1
+
+__device__ __forceinline__ uint32_t byte1(uint32_t v) { return __byte_perm(v, 0u, 0x4441); }   // (v >> 8) & 0xFF in one PRMT
+__device__ __forceinline__ uint32_t byte2(uint32_t v) { return __byte_perm(v, 0u, 0x4442); }
+
+template <int CHANS>
+__device__ __forceinline__ uint32_t literal_bits16(const uint8_t* s_lit, uint32_t px)
+{
+    uint32_t b = s_lit[px & 0xFFu] + s_lit[byte1(px)];
+    if (CHANS == 4) b += s_lit[byte2(px)] + s_lit[px >> 24];
+    else b += s_lit[px >> 16];
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (v2): per-row bit count + Adler partials (+ per-lane bit offsets inside the row for the pack kernel)
+// ------------------------------------------------------------------------------------------------
+template <int CHANS>
+__global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams p)
+{
+    constexpr uint32_t M = max_match_pixels(CHANS);
+    __shared__ __align__(16) uint8_t s_tile[kScan16Rows][kTileBytes];
+    __shared__ uint8_t s_lit[256];
+    __shared__ uint8_t s_match[88];
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t img = blockIdx.y;
+    const uint32_t y = blockIdx.x * kScan16Rows + warp;
+    const CodeBook* book = p.books + (size_t)img * p.book_stride;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = book->lit_size[i];
+    if (threadIdx.x < 88) s_match[threadIdx.x] = book->match_bits[threadIdx.x];
+    __syncthreads();
+    if (y >= p.h) return;
+
+    const uint32_t w = p.w, bpl = w * CHANS;
+    const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
+    const uint8_t* prev = y ? cur - bpl : nullptr;
+    const uint32_t filt = y ? 2u : 0u;
+    const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
+    uint8_t* tile = s_tile[warp];
+    uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
+
+    Walk16<CHANS> wk; wk.init(lane);
+    RowCarry carry = {0u, 0u};
+    uint32_t row_run = s_lit[filt];              // bits of the row emitted before the current step (filter literal first)
+    uint32_t sumA = 0, last_unit = 0;
+    unsigned long long sumB = 0;
+
+    for (uint32_t step = 0; step < nsteps; step++) {
+        uint32_t dw[Walk16<CHANS>::kWords], px[16];
+        wk.template load_step<true>(cur, prev, step, bpl, lane, tile, dw, sumA, sumB);
+        Walk16<CHANS>::pixels(dw, px);
+        const uint32_t p0 = step * kStep16 + lane * kPix16;
+        const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
+
+        uint32_t bits = 0;
+        // literal pixels: sum of code sizes.  Warp-uniform fast paths: no literal at all (RLE rows) / all literal (noisy rows)
+        const uint32_t any_lit = __any_sync(kFullMask, t.litm != 0);
+        if (any_lit) {
+            if (__all_sync(kFullMask, t.litm == 0xFFFFu)) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) bits += literal_bits16<CHANS>(s_lit, px[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t c = literal_bits16<CHANS>(s_lit, px[k]);
+                    bits += (t.litm & (1u << k)) ? c : 0u;
+                }
+            }
+        }
+        // match tokens: walk the runs of the 16-bit equality mask
+        uint32_t r = t.run, pos = 0;
+        const uint32_t nvp = t.nvp;
+        if (t.eqm | r) {
+            while (pos < nvp) {
+                const uint32_t m = t.eqm >> pos;
+                const uint32_t ones = min((uint32_t)__ffs((int)~m) - 1u, nvp - pos);     // leading equal pixels
+                if (ones) {
+                    r += ones; pos += ones;
+                    if (r >= M) { bits += s_match[M]; r -= M; }
+                    if (pos >= nvp) break;
+                }
+                if (r) { bits += s_match[r]; r = 0; }                                     // a literal follows: flush the remainder
+                const uint32_t mz = t.eqm >> pos;
+                const uint32_t zeros = mz ? (uint32_t)__ffs((int)mz) - 1u : 32u;
+                pos += zeros;
+            }
+        }
+        if (t.last) {
+            if (r) bits += s_match[r];
+            // capacity rule: size of the scanline's last flush unit
+            const uint32_t k = nvp - 1u;
+            if (t.litm & (1u << k)) {
+                uint32_t lastpx = px[0];
+#pragma unroll
+                for (int q = 1; q < 16; q++) lastpx = (k == (uint32_t)q) ? px[q] : lastpx;
+                last_unit = literal_bits16<CHANS>(s_lit, lastpx) + ((w == 1 && p.merge_first_unit) ? s_lit[filt] : 0u);
+            } else last_unit = r ? s_match[r] : s_match[M];
+            if (y == p.h - 1) p.st[img].last_unit_bits = last_unit;
+        }
+        // bit offset of this lane's first token inside the row (the pack kernel starts writing there)
+        uint32_t step_bits;
+        const uint32_t ex = warp_excl_scan_u32(bits, lane, step_bits);
+        lane_ofs[step * 32u + lane] = row_run + ex;
+        row_run += step_bits;
+    }
+
+    const unsigned long long A = warp_sum_u64(sumA);
+    const unsigned long long B = warp_sum_u64(sumB);
+    if (lane == 0) {
+        const unsigned long long n = (unsigned long long)bpl + 1ull;
+        const unsigned long long S1 = A + filt;
+        const unsigned long long S2 = n * S1 - (A + B);
+        p.row_bits[(size_t)img * p.h + y] = row_run;
+        p.row_adler[(size_t)img * p.h + y] = make_uint2((uint32_t)(S1 % kAdlerMod), (uint32_t)(S2 % kAdlerMod));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (v2): pack.  Every lane knows where its 16 pixels' tokens start (lane_ofs from the scan kernel), so it emits its
+// codes with a 64-bit accumulator straight into the warp's staging words: complete words with plain stores (they hold
+// only this lane's bits), its first word through a side slot and its last partial word with atomicOr.
+// ------------------------------------------------------------------------------------------------
+struct BitStager16 {
+    uint32_t* stage;            // warp staging words (zero outside the live range)
+    uint32_t* side;             // this lane's private slot for its first (shared) word
+    unsigned long long acc;
+    uint32_t nacc, wpos, firstw;
+    __device__ __forceinline__ void begin(uint32_t bitpos) { acc = 0; nacc = bitpos & 31u; wpos = firstw = bitpos >> 5; }
+    // append `len` (<= 32) bits; nacc < 32 on entry.  acc has no bits at or above nacc, so add == or and the shift can
+    // be done as a widening multiply-add on the FMA pipe.
+    __device__ __forceinline__ void put(uint32_t code, uint32_t len)
+    {
+        acc = (unsigned long long)code * (unsigned long long)(1u << nacc) + acc;
+        nacc += len;
+        const uint32_t f = nacc >> 5;                                   // 1 when the low word is complete
+        uint32_t* dst = (wpos == firstw) ? side : stage + wpos;
+        if (f) *dst = (uint32_t)acc;
+        acc >>= (f << 5);
+        nacc &= 31u;
+        wpos += f;
+    }
+    __device__ __forceinline__ void end()
+    {
+        if (wpos == firstw) { if ((uint32_t)acc) atomicOr(&stage[firstw], (uint32_t)acc); }       // everything fits in the first word
+        else {
+            atomicOr(&stage[firstw], *side);
+            if ((uint32_t)acc) atomicOr(&stage[wpos], (uint32_t)acc);
+        }
+    }
+};
+
+template <int CHANS>
+__device__ __forceinline__ void put_literal16(BitStager16& bs, const uint32_t* s_lit, uint32_t px)
+{
+    const uint32_t c0 = s_lit[px & 0xFFu], c1 = s_lit[byte1(px)];
+    const uint32_t l0 = c0 >> 16, l1 = c1 >> 16;
+    const uint32_t lo = (c0 & 0xFFFFu) | ((c1 & 0xFFFFu) << l0);                 // <= 24 bits
+    bs.put(lo, l0 + l1);
+    if (CHANS == 4) {
+        const uint32_t c2 = s_lit[byte2(px)], c3 = s_lit[px >> 24];
+        const uint32_t l2 = c2 >> 16, l3 = c3 >> 16;
+        bs.put((c2 & 0xFFFFu) | ((c3 & 0xFFFFu) << l2), l2 + l3);
+    } else {
+        const uint32_t c2 = s_lit[px >> 16];
+        bs.put(c2 & 0xFFFFu, c2 >> 16);
+    }
+}
+
+template <int CHANS>
+__global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParams p)
+{
+    constexpr uint32_t M = max_match_pixels(CHANS);
+    __shared__ __align__(16) uint8_t s_tile[kPack16Rows][kTileBytes];
+    __shared__ uint32_t s_lit[256];
+    __shared__ uint32_t s_match[88];
+    __shared__ uint32_t s_stage[kPack16Rows][kStage16Words];
+    __shared__ uint32_t s_side[kPack16Rows][32];
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t img = blockIdx.y;
+    const uint32_t y = blockIdx.x * kPack16Rows + warp;
+    const CodeBook* book = p.books + (size_t)img * p.book_stride;
+    const ImageState st = p.st[img];
+    if (st.stored) {                             // stored-block fallback (fpng.cpp:818-866): strided copy of this row
+        if (y < p.h) {
+            const uint32_t bpl_s = p.w * CHANS;
+            store_row_raw(p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl_s, p.out + (size_t)img * p.out_stride + kPngHeaderSize,
+                          y, bpl_s, lane, &p.row_adler[(size_t)img * p.h + y]);
+        }
+        return;
+    }
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = book->lit[i];
+    if (threadIdx.x < 88) s_match[threadIdx.x] = book->match[threadIdx.x];
+    for (uint32_t i = lane; i < kStage16Words; i += 32) s_stage[warp][i] = 0u;
+    __syncthreads();
+    if (y >= p.h) return;
+
+    const uint32_t w = p.w, bpl = w * CHANS;
+    const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
+    const uint8_t* prev = y ? cur - bpl : nullptr;
+    uint32_t* file_words = reinterpret_cast<uint32_t*>(p.out + (size_t)img * p.out_stride);
+    uint32_t* stage = s_stage[warp];
+    uint8_t* tile = s_tile[warp];
+    const uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
+    const uint32_t row_total = p.row_bits[(size_t)img * p.h + y];
+    const unsigned long long G = p.row_ofs[(size_t)img * p.h + y];
+    const unsigned long long first_word = G >> 5;
+    unsigned long long gword = first_word;       // global word that stage[0] maps to
+    const uint32_t g31 = (uint32_t)(G & 31ull);
+    uint32_t flushed_bits = 0;                   // row bits (incl. the G & 31 lead-in) already flushed to global, multiple of 32
+    const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
+    const uint32_t fcode = s_lit[y ? 2 : 0];
+
+    Walk16<CHANS> wk; wk.init(lane);
+    RowCarry carry = {0u, 0u};
+    uint32_t dummyA = 0; unsigned long long dummyB = 0;
+    for (uint32_t step = 0; step < nsteps; step++) {
+        uint32_t dw[Walk16<CHANS>::kWords], px[16];
+        wk.template load_step<false>(cur, prev, step, bpl, lane, tile, dw, dummyA, dummyB);
+        Walk16<CHANS>::pixels(dw, px);
+        const uint32_t p0 = step * kStep16 + lane * kPix16;
+        const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
+        const uint32_t my_ofs = lane_ofs[step * 32u + lane];
+        const uint32_t step_end = (step + 1 < nsteps) ? lane_ofs[(step + 1) * 32u] : row_total;   // row bits after this step
+
+        BitStager16 bs; bs.stage = stage; bs.side = &s_side[warp][lane];
+        // staging bit 0 corresponds to row bit (flushed_bits - g31); the filter literal sits at row bit 0
+        if (step == 0 && lane == 0) { bs.begin(g31); bs.put(fcode & 0xFFFFu, fcode >> 16); }
+        else bs.begin(g31 + my_ofs - flushed_bits);
+        uint32_t r = t.run;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if ((uint32_t)k < t.nvp) {
+                if (t.eqm & (1u << k)) {
+                    if (++r == M) { const uint32_t m = s_match[M]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
+                } else {
+                    if (r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
+                    put_literal16<CHANS>(bs, s_lit, px[k]);
+                }
+            }
+        }
+        if (t.last && r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); }
+        bs.end();
+        __syncwarp();
+
+        // ---- flush whole words; the row's first word is shared with the previous row / the block header
+        const uint32_t fill = g31 + step_end - flushed_bits;            // live bits in the staging buffer
+        const uint32_t nwords = fill >> 5;
+        const uint32_t leftover = stage[nwords];
+        for (uint32_t j = lane; j < nwords; j += 32) {
+            const uint32_t v = stage[j];
+            if (gword + j == first_word) atomicOr(&file_words[gword + j], v);
+            else file_words[gword + j] = v;
+        }
+        __syncwarp();
+        for (uint32_t j = lane; j <= nwords; j += 32) stage[j] = (j == 0) ? leftover : 0u;
+        __syncwarp();
+        gword += nwords;
+        flushed_bits += nwords << 5;
+    }
+    if (lane == 0) {
+        const uint32_t v = stage[0];
+        if (v) atomicOr(&file_words[gword], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t chans)
+{
+    const size_t bpl = (size_t)w * chans;
+    return ((uintptr_t)base % 16 == 0) && (image_stride % 16 == 0) && (bpl % 16 == 0);
+}
+
+void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
+{
+    dim3 grid((p.h + kScan16Rows - 1) / kScan16Rows, n);
+    if (chans == 4) row_scan16_kernel<4><<<grid, 32 * kScan16Rows, 0, s>>>(p);
+    else row_scan16_kernel<3><<<grid, 32 * kScan16Rows, 0, s>>>(p);
+}
+
+void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
+{
+    dim3 grid((p.h + kPack16Rows - 1) / kPack16Rows, n);
+    if (chans == 4) pack_rows16_kernel<4><<<grid, 32 * kPack16Rows, 0, s>>>(p);
+    else pack_rows16_kernel<3><<<grid, 32 * kPack16Rows, 0, s>>>(p);
+}
+
+}  // namespace fpngb

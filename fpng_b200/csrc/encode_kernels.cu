@@ -288,24 +288,6 @@ __device__ __forceinline__ uint32_t literal_bits_w(const uint32_t* s_lit, uint32
     return b;
 }
 
-// Stored-block fallback for one row: stream byte s (row y, column t; t == 0 is the filter byte 0) lands at
-// zlib offset 2 + 5 * (s / 65535 + 1) + s.  Also produces the row's Adler partials over the raw bytes.
-__device__ __forceinline__ void store_row_raw(const uint8_t* __restrict__ cur, uint8_t* __restrict__ zl, uint32_t y, uint32_t bpl,
-                                              uint32_t lane, uint2* adler_out)
-{
-    const unsigned long long n = (unsigned long long)bpl + 1ull;
-    const unsigned long long s0 = (unsigned long long)y * n;
-    unsigned long long A = 0, B = 0;
-    for (unsigned long long t = lane; t < n; t += 32) {
-        const uint32_t v = t ? ld_u8(cur + (t - 1)) : 0u;
-        const unsigned long long s = s0 + t;
-        zl[2ull + 5ull * (s / 65535ull + 1ull) + s] = (uint8_t)v;
-        A += v; B += t * v;
-    }
-    A = warp_sum_u64(A); B = warp_sum_u64(B);
-    if (lane == 0) *adler_out = make_uint2((uint32_t)(A % kAdlerMod), (uint32_t)((n * A - B) % kAdlerMod));
-}
-
 template <int CHANS, int MODE>
 __global__ void __launch_bounds__(kPackThreads) pack_rows_kernel(PackParams p)
 {

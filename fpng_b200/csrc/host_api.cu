@@ -14,6 +14,7 @@
 #include <atomic>
 #include <mutex>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -159,12 +160,14 @@ static void prof_mark(ProfSet* ps, int slot, cudaStream_t s)
 
 struct Workspace {
     uint32_t* row_bits; uint2* row_adler; unsigned long long* row_ofs; ImageState* st; uint32_t* hist; CodeBook* books;
+    uint32_t* lane_ofs; uint32_t lane_ofs_pitch;
 };
 
 
-static int carve_workspace(Context& c, uint32_t n, uint32_t h, bool two_pass, Workspace& w)
+static int carve_workspace(Context& c, uint32_t n, uint32_t h, uint32_t width, bool two_pass, Workspace& w)
 {
     const size_t rows = (size_t)n * h;
+    const uint32_t lane_pitch = ((width + 511u) / 512u) * 32u;       // one u32 per 16-pixel group, whole warp steps
     size_t o = 0;
     const size_t o_bits = o; o = align_up(o + rows * 4, 256);
     const size_t o_adl = o; o = align_up(o + rows * 8, 256);
@@ -172,11 +175,13 @@ static int carve_workspace(Context& c, uint32_t n, uint32_t h, bool two_pass, Wo
     const size_t o_st = o; o = align_up(o + (size_t)n * sizeof(ImageState), 256);
     const size_t o_hist = o; o = align_up(o + (two_pass ? (size_t)n * 288 * 4 : 0), 256);
     const size_t o_books = o; o = align_up(o + (two_pass ? (size_t)n * sizeof(CodeBook) : 0), 256);
+    const size_t o_lane = o; o = align_up(o + rows * lane_pitch * 4, 256);
     int rc = c.ws.reserve(o);
     if (rc) return rc;
     uint8_t* b = (uint8_t*)c.ws.p;
     w.row_bits = (uint32_t*)(b + o_bits); w.row_adler = (uint2*)(b + o_adl); w.row_ofs = (unsigned long long*)(b + o_ofs);
     w.st = (ImageState*)(b + o_st); w.hist = (uint32_t*)(b + o_hist); w.books = (CodeBook*)(b + o_books);
+    w.lane_ofs = (uint32_t*)(b + o_lane); w.lane_ofs_pitch = lane_pitch;
     return 0;
 }
 
@@ -225,9 +230,13 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
 {
     const bool two_pass = (flags & FPNGB_ENCODE_SLOWER) && !(flags & FPNGB_FORCE_UNCOMPRESSED);
     Workspace ws;
-    int rc = carve_workspace(c, n, h, two_pass, ws);
+    int rc = carve_workspace(c, n, h, w, two_pass, ws);
     if (rc) return rc;
     const int mode = pick_load_mode(d_pixels, image_stride, w, chans);
+    // second-generation kernels (16 pixels per lane, coalesced 128-bit loads) whenever every scanline is 16-byte aligned;
+    // FPNGB_FORCE_GENERIC=1 keeps the generic kernels (tests compare both)
+    static const bool force_generic = getenv("FPNGB_FORCE_GENERIC") && atoi(getenv("FPNGB_FORCE_GENERIC")) != 0;
+    const bool v2 = !force_generic && walk16_eligible(d_pixels, image_stride, w, chans);
     const CodeBook* books = two_pass ? ws.books : c.d_static_books + (chans == 4 ? 1 : 0);
     const uint32_t book_stride = two_pass ? 1u : 0u;
 
@@ -236,6 +245,7 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     sp.books = books; sp.book_stride = book_stride;
     sp.row_bits = ws.row_bits; sp.row_adler = ws.row_adler; sp.st = ws.st; sp.hist = ws.hist;
     sp.merge_first_unit = (!two_pass && chans == 3) ? 1u : 0u;
+    sp.lane_ofs = ws.lane_ofs; sp.lane_ofs_pitch = ws.lane_ofs_pitch;
 
     ProfSet* ps = prof_begin(s);
     if (two_pass) {
@@ -247,7 +257,7 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
         prof_mark(ps, kProfHuff, s);
         count_launch(2);
     }
-    launch_scan(sp, n, chans, mode, false, s);
+    if (v2) launch_scan16(sp, n, chans, s); else launch_scan(sp, n, chans, mode, false, s);
     prof_mark(ps, kProfScan, s);
 
     OffsetsParams op{};
@@ -259,8 +269,8 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
 
     PackParams pp{};
     pp.pixels = d_pixels; pp.image_stride = image_stride; pp.w = w; pp.h = h; pp.books = books; pp.book_stride = book_stride;
-    pp.row_ofs = ws.row_ofs; pp.row_adler = ws.row_adler; pp.st = ws.st; pp.out = d_out; pp.out_stride = out_stride;
-    launch_pack(pp, n, chans, mode, s);
+    pp.row_ofs = ws.row_ofs; pp.row_bits = ws.row_bits; pp.lane_ofs = ws.lane_ofs; pp.lane_ofs_pitch = ws.lane_ofs_pitch; pp.row_adler = ws.row_adler; pp.st = ws.st; pp.out = d_out; pp.out_stride = out_stride;
+    if (v2) launch_pack16(pp, n, chans, s); else launch_pack(pp, n, chans, mode, s);
     prof_mark(ps, kProfPack, s);
 
     AdlerParams ap{ws.row_adler, ws.st, d_out, out_stride, w, h, chans};

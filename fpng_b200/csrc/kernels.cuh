@@ -19,6 +19,7 @@ struct ScanParams {
     ImageState* st;                               // [n]
     uint32_t* hist;                               // [n*288] (histogram mode)
     uint32_t merge_first_unit;                    // RGB 1-pass: filter literal and pixel 0 share a flush unit (fpng.cpp:1187-1203)
+    uint32_t* lane_ofs; uint32_t lane_ofs_pitch;  // v2 kernels: [n*h][pitch] bit offset of every 16-pixel group inside its row
 };
 
 struct OffsetsParams {
@@ -35,6 +36,8 @@ struct PackParams {
     uint32_t w, h;
     const CodeBook* books; uint32_t book_stride;
     const unsigned long long* row_ofs;
+    const uint32_t* row_bits;                     // v2 kernels: total token bits per row
+    const uint32_t* lane_ofs; uint32_t lane_ofs_pitch;
     uint2* row_adler;                             // rewritten for stored images (raw bytes, filter 0)
     const ImageState* st;
     uint8_t* out; size_t out_stride;
@@ -61,6 +64,9 @@ struct HuffParams {
 };
 
 void launch_scan(const ScanParams& p, uint32_t n, uint32_t chans, int mode, bool hist, cudaStream_t s);
+bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t chans);
+void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s);
+void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s);
 void launch_offsets(const OffsetsParams& p, uint32_t n, cudaStream_t s);
 void launch_pack(const PackParams& p, uint32_t n, uint32_t chans, int mode, cudaStream_t s);
 void launch_adler_finalize(const AdlerParams& p, uint32_t n, cudaStream_t s);

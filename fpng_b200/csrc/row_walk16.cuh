@@ -1,0 +1,134 @@
+// fpng_b200/csrc/row_walk16.cuh -- second-generation scanline walker: 16 consecutive pixels per lane, 512 per warp step.
+//
+// Same tokenisation as row_walk.cuh (reference: fpng.cpp:1182-1243 / 1468-1558) with the
+// per-step warp-wide work (neighbour shuffle, ballot, run phase) amortised over 4x more pixels and with fully coalesced
+// 128-bit global loads:
+//   1. lane l loads uint4 #(j*32 + l), j = 0..CHANS-1, of the step's cur and prev scanline bytes (coalesced),
+//      subtracts (PNG filter 2 "Up", fpng.cpp:1605-1652) and accumulates the Adler-32 partial sums on the spot
+//      (position-weighted sums are layout independent);
+//   2. the filtered 16-byte chunks go through a padded shared-memory tile (80 bytes per lane: conflict-free 128-bit
+//      reads) so that each lane ends up with its own 16 consecutive pixels in registers;
+//   3. equality with the left pixel gives a 16-bit mask per lane; the run phase entering the lane is one ballot + one
+//      shuffle; the lane then walks its pixels.
+// Requires every scanline to start 16-byte aligned and bpl % 16 == 0 (RGBA: w % 4 == 0, RGB: w % 16 == 0); other
+// shapes use the generic kernels of row_walk.cuh.
+#pragma once
+#include "row_walk.cuh"
+
+namespace fpngb {
+
+constexpr int kPix16 = 16;                       // pixels per lane per step
+constexpr int kStep16 = 32 * kPix16;             // pixels per warp step
+constexpr int kTileLaneBytes = 80;               // padded per-lane slot in the transpose tile
+constexpr int kTileBytes = 32 * kTileLaneBytes;  // per warp
+
+template <int CHANS>
+struct Walk16 {
+    static constexpr int kWords = 4 * CHANS;     // filtered words per lane per step (16 pixels)
+    uint32_t soff[CHANS];                        // byte offsets inside the warp tile where this lane stores its chunks
+
+    __device__ __forceinline__ void init(uint32_t lane)
+    {
+#pragma unroll
+        for (int j = 0; j < CHANS; j++) {
+            const uint32_t q = j * 32u + lane;   // chunk index inside the step
+            soff[j] = (q / CHANS) * kTileLaneBytes + (q % CHANS) * 16u;
+        }
+    }
+
+    // Loads + filters one step; returns the lane's 16 pixels (dw: filtered bytes in memory order) and adds the step's
+    // Adler partials (sum of bytes, position-weighted sum) to sumA / sumB.
+    template <bool kAdler>
+    __device__ __forceinline__ void load_step(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev, uint32_t step, uint32_t bpl,
+                                              uint32_t lane, uint8_t* tile /*this warp's kTileBytes*/, uint32_t (&dw)[kWords],
+                                              uint32_t& sumA, unsigned long long& sumB)
+    {
+        const uint32_t step_base = step * (uint32_t)(kStep16 * CHANS);
+#pragma unroll
+        for (int j = 0; j < CHANS; j++) {
+            const uint32_t b = step_base + (j * 32u + lane) * 16u;
+            uint4 d = make_uint4(0, 0, 0, 0);
+            if (b < bpl) {
+                const uint4 c = __ldg(reinterpret_cast<const uint4*>(cur + b));
+                if (prev) {
+                    const uint4 p = __ldg(reinterpret_cast<const uint4*>(prev + b));
+                    d.x = vsub4(c.x, p.x); d.y = vsub4(c.y, p.y); d.z = vsub4(c.z, p.z); d.w = vsub4(c.w, p.w);
+                } else d = c;
+                if (kAdler) {
+                    uint32_t t1 = __dp4a(d.x, 0x01010101u, 0u), t2 = __dp4a(d.x, 0x03020100u, 0u);
+                    t1 = __dp4a(d.y, 0x01010101u, t1); t2 = __dp4a(d.y, 0x07060504u, t2);
+                    t1 = __dp4a(d.z, 0x01010101u, t1); t2 = __dp4a(d.z, 0x0B0A0908u, t2);
+                    t1 = __dp4a(d.w, 0x01010101u, t1); t2 = __dp4a(d.w, 0x0F0E0D0Cu, t2);
+                    sumA += t1;
+                    sumB += (unsigned long long)b * t1 + t2;
+                }
+            }
+            *reinterpret_cast<uint4*>(tile + soff[j]) = d;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < CHANS; i++) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + lane * kTileLaneBytes + i * 16);
+            dw[4 * i] = v.x; dw[4 * i + 1] = v.y; dw[4 * i + 2] = v.z; dw[4 * i + 3] = v.w;
+        }
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ static void pixels(const uint32_t (&dw)[kWords], uint32_t (&px)[16])
+    {
+        if (CHANS == 4) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) px[k] = dw[k];
+        } else {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const uint32_t w0 = dw[3 * g], w1 = dw[3 * g + 1], w2 = dw[3 * g + 2];
+                px[4 * g] = w0 & 0x00FFFFFFu;
+                px[4 * g + 1] = __byte_perm(w0, w1, 0x4543) & 0x00FFFFFFu;
+                px[4 * g + 2] = __byte_perm(w1, w2, 0x4432) & 0x00FFFFFFu;
+                px[4 * g + 3] = w2 >> 8;
+            }
+        }
+    }
+};
+
+struct Lane16 {
+    uint32_t eqm;      // bit k: pixel k equals its left neighbour (valid pixels only)
+    uint32_t litm;     // bit k: pixel k is a literal
+    uint32_t nvp;      // valid pixels in this lane (0..16)
+    uint32_t run;      // pending (unfinished) match length entering the lane, 0..M-1
+    bool last;         // this lane holds the scanline's last pixel
+};
+
+template <int CHANS>
+__device__ __forceinline__ Lane16 classify16(const uint32_t (&px)[16], uint32_t p0, uint32_t w, RowCarry& carry, uint32_t lane)
+{
+    constexpr uint32_t M = max_match_pixels(CHANS);
+    Lane16 t;
+    t.nvp = p0 < w ? min(16u, w - p0) : 0u;
+    uint32_t left = __shfl_up_sync(kFullMask, px[15], 1);
+    if (lane == 0) left = carry.prev_px;
+    uint32_t eq = (p0 > 0 && px[0] == left) ? 1u : 0u;
+#pragma unroll
+    for (int k = 1; k < 16; k++) eq |= (px[k] == px[k - 1]) ? (1u << k) : 0u;
+    const uint32_t valid = (1u << t.nvp) - 1u;
+    t.eqm = eq & valid;
+    t.litm = valid & ~eq;
+    t.last = t.nvp > 0 && p0 + t.nvp == w;
+
+    const uint32_t trail = t.litm ? (t.nvp - 1u - (31u - (uint32_t)__clz((int)t.litm))) : t.nvp;
+    const uint32_t has_lit = __ballot_sync(kFullMask, t.litm != 0);
+    const uint32_t lower = has_lit & ((1u << lane) - 1u);
+    const uint32_t src = lower ? (31u - (uint32_t)__clz((int)lower)) : 0u;
+    const uint32_t src_trail = __shfl_sync(kFullMask, trail, src);
+    const uint32_t run = lower ? (src_trail + 16u * (lane - src - 1u)) : (carry.run + 16u * lane);
+    t.run = run % M;
+
+    // carry for the next step: what lane 31 leaves pending
+    const uint32_t out_run = t.litm ? trail : (t.run + t.nvp) % M;     // all-equal lane: phase advances by nvp
+    carry.prev_px = __shfl_sync(kFullMask, px[15], 31);
+    carry.run = __shfl_sync(kFullMask, out_run, 31);
+    return t;
+}
+
+}  // namespace fpngb

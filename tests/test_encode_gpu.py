@@ -13,7 +13,8 @@ from common import golden_vectors, sha
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(1, 1), (1, 9), (2, 2), (5, 3), (15, 2), (16, 2), (20, 1), (24, 1), (63, 3), (64, 3), (65, 3), (85, 2), (86, 2), (127, 5),
-          (128, 4), (129, 6), (255, 3), (256, 3), (257, 33), (340, 5), (512, 64), (687, 41), (1000, 3), (2049, 2)]
+          (128, 4), (129, 6), (255, 3), (256, 3), (257, 33), (340, 5), (512, 64), (687, 41), (1000, 3), (2049, 2),
+          (528, 3), (1024, 5), (1040, 2), (1920, 3), (4096, 2), (8192, 1)]   # multi-step rows on the 16-pixel-per-lane kernels
 
 
 @pytest.mark.parametrize("kind", ["g0", "g1", "g2", "runs", "mut", "zero"])
@@ -146,3 +147,32 @@ def test_checksum_utilities(gpu, oracle):
         assert gpu.fpng_adler32(d, 0x00030002) == oracle.adler32(d, 0x00030002), n
     assert gpu.fpng_crc32(b"123456789") == 0xCBF43926
     assert gpu.fpng_adler32(b"Wikipedia") == 0x11E60398
+
+
+def test_generic_kernels_still_match(oracle):
+    """The second-generation kernels are the default for 16-byte aligned scanlines; FPNGB_FORCE_GENERIC=1 selects the
+    generic kernels for the same shapes.  Both must produce the reference bytes (run in a subprocess: the switch is read once)."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, os
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'tests'))
+import imagegen, fpng_b200
+from oracle.pyoracle import Oracle
+o = Oracle(); fpng_b200.fpng_init()
+bad = 0
+for kind in ('g1', 'g0', 'runs', 'g2'):
+    for (w, h) in ((16, 2), (512, 9), (1024, 5), (1920, 3), (4096, 2)):
+        for c in (3, 4):
+            img = imagegen.make(kind, w, h, c, 3)
+            for flags in (0, 1):
+                ok, png = fpng_b200.fpng_encode_image_to_memory(img, w, h, c, flags)
+                bad += (not ok) or png != o.encode(img, w, h, c, flags)
+print('bad', bad)
+sys.exit(1 if bad else 0)
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FPNGB_FORCE_GENERIC="1")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
