@@ -28,6 +28,7 @@ __constant__ uint32_t c_xinvpow2[64];               // x^-(2^k) mod P
 __constant__ uint32_t c_level[8];                   // x^(8 * 128 * 2^k): chunk-combine multipliers
 __constant__ uint32_t c_tile;                       // x^(8 * kTileBytes)
 __device__ uint32_t g_crc_tables[4][256];           // slice-by-4
+__device__ uint32_t g_crc_mul[8][8][16];            // g_crc_mul[k][j][n] = (n << 4j) * x^(8*128*2^k) mod P: multiply-by-constant as 8 nibble lookups
 
 __host__ __device__ inline uint32_t gf2_mulmod(uint32_t a, uint32_t b)
 {
@@ -87,6 +88,9 @@ int checksum_tables_init()
     FPNGB_CUDA_OK(cudaMemcpyToSymbol(c_level, lvl, sizeof lvl));
     FPNGB_CUDA_OK(cudaMemcpyToSymbol(c_tile, &tile, sizeof tile));
     FPNGB_CUDA_OK(cudaMemcpyToSymbol(g_crc_tables, h_tables, sizeof h_tables));
+    static uint32_t mul[8][8][16];
+    for (int k = 0; k < 8; k++) for (int j = 0; j < 8; j++) for (uint32_t n = 0; n < 16; n++) mul[k][j][n] = gf2_mulmod(n << (4 * j), lvl[k]);
+    FPNGB_CUDA_OK(cudaMemcpyToSymbol(g_crc_mul, mul, sizeof mul));
     return 0;
 }
 
@@ -109,9 +113,19 @@ __device__ __forceinline__ uint32_t condition_word(uint32_t v, uint32_t wo, uint
     return (v ^ inv) & keep;
 }
 
+// a * x^(8*128*2^k) mod P through the level's nibble tables (GF(2)-linear in a)
+__device__ __forceinline__ uint32_t mul_level(const uint32_t (*t)[16], uint32_t a)
+{
+    uint32_t r = t[0][a & 15u];
+#pragma unroll
+    for (int j = 1; j < 8; j++) r ^= t[j][(a >> (4 * j)) & 15u];
+    return r;
+}
+
 __global__ void __launch_bounds__(kCrcThreads) idat_crc_kernel(CrcParams p)
 {
     __shared__ uint32_t s_tab[4][256];
+    __shared__ uint32_t s_mul[8][8][16];
     __shared__ uint32_t s_data[kCrcThreads * (kChunkWords + 1)];
     __shared__ uint32_t s_warp[kCrcThreads / 32];
 
@@ -123,7 +137,7 @@ __global__ void __launch_bounds__(kCrcThreads) idat_crc_kernel(CrcParams p)
     const uint32_t nctas = (ntiles + kTilesPerCta - 1) / kTilesPerCta;
     if (b >= nctas) return;
 
-    for (uint32_t i = tid; i < 1024; i += blockDim.x) (&s_tab[0][0])[i] = (&g_crc_tables[0][0])[i];
+    for (uint32_t i = tid; i < 1024; i += blockDim.x) { (&s_tab[0][0])[i] = (&g_crc_tables[0][0])[i]; (&s_mul[0][0][0])[i] = (&g_crc_mul[0][0][0])[i]; }
 
     const uint8_t* file = p.out + (size_t)img * p.out_stride;
     const uint32_t t0 = b * kTilesPerCta, t1 = min(t0 + kTilesPerCta, ntiles);
@@ -133,15 +147,22 @@ __global__ void __launch_bounds__(kCrcThreads) idat_crc_kernel(CrcParams p)
         const uint32_t tile_ofs = tile * kTileBytes;
         __syncthreads();
         // coalesced 16-byte loads -> padded shared layout (chunk c at words [33c, 33c+32))
+        // tiles strictly inside the message need no conditioning (only the first and last tile of a file do)
+        const bool interior = tile_ofs >= start + 4u && tile_ofs + kTileBytes <= L;
         for (uint32_t g = tid; g < kTileWords / 4; g += blockDim.x) {
             const uint32_t wo = tile_ofs + g * 16u;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (wo < L) v = *reinterpret_cast<const uint4*>(file + wo);
             const uint32_t wi = g * 4u, base = (wi / kChunkWords) * (kChunkWords + 1) + (wi % kChunkWords);
-            s_data[base + 0] = condition_word(v.x, wo, start, L, init);
-            s_data[base + 1] = condition_word(v.y, wo + 4u, start, L, init);
-            s_data[base + 2] = condition_word(v.z, wo + 8u, start, L, init);
-            s_data[base + 3] = condition_word(v.w, wo + 12u, start, L, init);
+            if (interior) {
+                const uint4 v = *reinterpret_cast<const uint4*>(file + wo);
+                s_data[base + 0] = v.x; s_data[base + 1] = v.y; s_data[base + 2] = v.z; s_data[base + 3] = v.w;
+            } else {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (wo < L) v = *reinterpret_cast<const uint4*>(file + wo);
+                s_data[base + 0] = condition_word(v.x, wo, start, L, init);
+                s_data[base + 1] = condition_word(v.y, wo + 4u, start, L, init);
+                s_data[base + 2] = condition_word(v.z, wo + 8u, start, L, init);
+                s_data[base + 3] = condition_word(v.w, wo + 12u, start, L, init);
+            }
         }
         __syncthreads();
 
@@ -156,7 +177,7 @@ __global__ void __launch_bounds__(kCrcThreads) idat_crc_kernel(CrcParams p)
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             const uint32_t right = __shfl_down_sync(0xFFFFFFFFu, crc, 1u << k);
-            const uint32_t prod = gf2_mulmod(crc, c_level[k]);
+            const uint32_t prod = mul_level(s_mul[k], crc);
             if ((lane & ((2u << k) - 1u)) == 0) crc = prod ^ right;
         }
         if (lane == 0) s_warp[warp] = crc;
@@ -166,7 +187,7 @@ __global__ void __launch_bounds__(kCrcThreads) idat_crc_kernel(CrcParams p)
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const uint32_t right = __shfl_down_sync(0xFFFFFFFFu, v, 1u << k);
-                const uint32_t prod = gf2_mulmod(v, c_level[5 + k]);
+                const uint32_t prod = mul_level(s_mul[5 + k], v);
                 if ((lane & ((2u << k) - 1u)) == 0) v = prod ^ right;
             }
             if (lane == 0) acc = gf2_mulmod(acc, c_tile) ^ v;

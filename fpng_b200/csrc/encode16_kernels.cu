@@ -29,9 +29,9 @@ template <int CHANS>
 __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams p)
 {
     constexpr uint32_t M = max_match_pixels(CHANS);
-    __shared__ __align__(16) uint8_t s_tile[kScan16Rows][kTileBytes];
-    __shared__ uint8_t s_lit[256];
-    __shared__ uint8_t s_match[88];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    uint8_t* s_lit = dyn_smem + kScan16Rows * kTileWarpBytes;
+    uint8_t* s_match = s_lit + 256;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t img = blockIdx.y;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
     const uint8_t* prev = y ? cur - bpl : nullptr;
     const uint32_t filt = y ? 2u : 0u;
     const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
-    uint8_t* tile = s_tile[warp];
+    uint8_t* tiles = dyn_smem + warp * kTileWarpBytes;
     uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
 
     Walk16<CHANS> wk; wk.init(lane);
@@ -56,9 +56,14 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
     uint32_t sumA = 0, last_unit = 0;
     unsigned long long sumB = 0;
 
+    wk.prefetch(cur, prev, 0, bpl, lane, tiles, 0);
     for (uint32_t step = 0; step < nsteps; step++) {
         uint32_t dw[Walk16<CHANS>::kWords], px[16];
-        wk.template load_step<true>(cur, prev, step, bpl, lane, tile, dw, sumA, sumB);
+        cp_async_wait<0>();
+        __syncwarp();
+        wk.template consume<true>(prev != nullptr, step, lane, tiles, 0, dw, sumA, sumB);
+        __syncwarp();
+        if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles, 0);      // lands while this step is processed
         Walk16<CHANS>::pixels(dw, px);
         const uint32_t p0 = step * kStep16 + lane * kPix16;
         const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
@@ -181,11 +186,11 @@ template <int CHANS>
 __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParams p)
 {
     constexpr uint32_t M = max_match_pixels(CHANS);
-    __shared__ __align__(16) uint8_t s_tile[kPack16Rows][kTileBytes];
-    __shared__ uint32_t s_lit[256];
-    __shared__ uint32_t s_match[88];
-    __shared__ uint32_t s_stage[kPack16Rows][kStage16Words];
-    __shared__ uint32_t s_side[kPack16Rows][32];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    uint32_t* s_lit = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * kTileWarpBytes);
+    uint32_t* s_match = s_lit + 256;
+    uint32_t* s_stage_all = s_match + 88;
+    uint32_t* s_side_all = s_stage_all + kPack16Rows * kStage16Words;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t img = blockIdx.y;
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     }
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = book->lit[i];
     if (threadIdx.x < 88) s_match[threadIdx.x] = book->match[threadIdx.x];
-    for (uint32_t i = lane; i < kStage16Words; i += 32) s_stage[warp][i] = 0u;
+    for (uint32_t i = lane; i < kStage16Words; i += 32) s_stage_all[warp * kStage16Words + i] = 0u;
     __syncthreads();
     if (y >= p.h) return;
 
@@ -210,8 +215,8 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
     const uint8_t* prev = y ? cur - bpl : nullptr;
     uint32_t* file_words = reinterpret_cast<uint32_t*>(p.out + (size_t)img * p.out_stride);
-    uint32_t* stage = s_stage[warp];
-    uint8_t* tile = s_tile[warp];
+    uint32_t* stage = s_stage_all + warp * kStage16Words;
+    uint8_t* tiles = dyn_smem + warp * kTileWarpBytes;
     const uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
     const uint32_t row_total = p.row_bits[(size_t)img * p.h + y];
     const unsigned long long G = p.row_ofs[(size_t)img * p.h + y];
@@ -225,16 +230,21 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     Walk16<CHANS> wk; wk.init(lane);
     RowCarry carry = {0u, 0u};
     uint32_t dummyA = 0; unsigned long long dummyB = 0;
+    wk.prefetch(cur, prev, 0, bpl, lane, tiles, 0);
     for (uint32_t step = 0; step < nsteps; step++) {
         uint32_t dw[Walk16<CHANS>::kWords], px[16];
-        wk.template load_step<false>(cur, prev, step, bpl, lane, tile, dw, dummyA, dummyB);
+        cp_async_wait<0>();
+        __syncwarp();
+        wk.template consume<false>(prev != nullptr, step, lane, tiles, 0, dw, dummyA, dummyB);
+        __syncwarp();
+        if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles, 0);      // lands while this step is emitted
         Walk16<CHANS>::pixels(dw, px);
         const uint32_t p0 = step * kStep16 + lane * kPix16;
         const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
         const uint32_t my_ofs = lane_ofs[step * 32u + lane];
         const uint32_t step_end = (step + 1 < nsteps) ? lane_ofs[(step + 1) * 32u] : row_total;   // row bits after this step
 
-        BitStager16 bs; bs.stage = stage; bs.side = &s_side[warp][lane];
+        BitStager16 bs; bs.stage = stage; bs.side = s_side_all + warp * 32 + lane;
         // staging bit 0 corresponds to row bit (flushed_bits - g31); the filter literal sits at row bit 0
         if (step == 0 && lane == 0) { bs.begin(g31); bs.put(fcode & 0xFFFFu, fcode >> 16); }
         else bs.begin(g31 + my_ofs - flushed_bits);
@@ -284,18 +294,25 @@ bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t
     return ((uintptr_t)base % 16 == 0) && (image_stride % 16 == 0) && (bpl % 16 == 0);
 }
 
+constexpr size_t kScan16Smem = kScan16Rows * kTileWarpBytes + 256 + 96;
+constexpr size_t kPack16Smem = kPack16Rows * kTileWarpBytes + (256 + 88 + kPack16Rows * kStage16Words + kPack16Rows * 32) * 4;
+
+// opt in to > 48 KiB of dynamic shared memory (per kernel instantiation, once per process)
+#define FPNGB_SET_SMEM(kernel, bytes) do { static bool done_ = false; \
+    if (!done_) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); done_ = true; } } while (0)
+
 void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
     dim3 grid((p.h + kScan16Rows - 1) / kScan16Rows, n);
-    if (chans == 4) row_scan16_kernel<4><<<grid, 32 * kScan16Rows, 0, s>>>(p);
-    else row_scan16_kernel<3><<<grid, 32 * kScan16Rows, 0, s>>>(p);
+    if (chans == 4) { FPNGB_SET_SMEM(row_scan16_kernel<4>, kScan16Smem); row_scan16_kernel<4><<<grid, 32 * kScan16Rows, kScan16Smem, s>>>(p); }
+    else { FPNGB_SET_SMEM(row_scan16_kernel<3>, kScan16Smem); row_scan16_kernel<3><<<grid, 32 * kScan16Rows, kScan16Smem, s>>>(p); }
 }
 
 void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
     dim3 grid((p.h + kPack16Rows - 1) / kPack16Rows, n);
-    if (chans == 4) pack_rows16_kernel<4><<<grid, 32 * kPack16Rows, 0, s>>>(p);
-    else pack_rows16_kernel<3><<<grid, 32 * kPack16Rows, 0, s>>>(p);
+    if (chans == 4) { FPNGB_SET_SMEM(pack_rows16_kernel<4>, kPack16Smem); pack_rows16_kernel<4><<<grid, 32 * kPack16Rows, kPack16Smem, s>>>(p); }
+    else { FPNGB_SET_SMEM(pack_rows16_kernel<3>, kPack16Smem); pack_rows16_kernel<3><<<grid, 32 * kPack16Rows, kPack16Smem, s>>>(p); }
 }
 
 }  // namespace fpngb

@@ -3,11 +3,10 @@
 // Same tokenisation as row_walk.cuh (reference: fpng.cpp:1182-1243 / 1468-1558) with the
 // per-step warp-wide work (neighbour shuffle, ballot, run phase) amortised over 4x more pixels and with fully coalesced
 // 128-bit global loads:
-//   1. lane l loads uint4 #(j*32 + l), j = 0..CHANS-1, of the step's cur and prev scanline bytes (coalesced),
-//      subtracts (PNG filter 2 "Up", fpng.cpp:1605-1652) and accumulates the Adler-32 partial sums on the spot
-//      (position-weighted sums are layout independent);
-//   2. the filtered 16-byte chunks go through a padded shared-memory tile (80 bytes per lane: conflict-free 128-bit
-//      reads) so that each lane ends up with its own 16 consecutive pixels in registers;
+//   1. lane l issues cp.async (LDGSTS) copies of the 16-byte chunks #(j*32 + l), j = 0..CHANS-1, of the step's cur and
+//      prev scanline bytes (coalesced in HBM) into a padded shared-memory tile, one step ahead of the computation;
+//   2. each lane reads its own 16 consecutive pixels (80-byte slots: conflict-free 128-bit reads), subtracts the previous
+//      scanline (PNG filter 2 "Up", fpng.cpp:1605-1652) and accumulates the Adler-32 partial sums;
 //   3. equality with the left pixel gives a 16-bit mask per lane; the run phase entering the lane is one ballot + one
 //      shuffle; the lane then walks its pixels.
 // Requires every scanline to start 16-byte aligned and bpl % 16 == 0 (RGBA: w % 4 == 0, RGB: w % 16 == 0); other
@@ -22,10 +21,26 @@ constexpr int kStep16 = 32 * kPix16;             // pixels per warp step
 constexpr int kTileLaneBytes = 80;               // padded per-lane slot in the transpose tile
 constexpr int kTileBytes = 32 * kTileLaneBytes;  // per warp
 
+constexpr int kTileStageBytes = 2 * kTileBytes;         // cur + prev tiles of one pipeline stage
+constexpr int kTileWarpBytes = kTileStageBytes;         // one stage: the next step is fetched as soon as this one is in registers
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int src_bytes = valid ? 16 : 0;                // 0 -> the 16 destination bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+// Scanline staging through shared memory with cp.async (LDGSTS): lane l copies the step's 16-byte chunks #(j*32 + l)
+// (coalesced in global memory) straight into the slot of the lane that owns those pixels (80-byte padded slots, so the
+// later 128-bit reads are bank-conflict free).  The tile is consumed into registers first, then refilled for step s+1
+// while step s is being processed.
 template <int CHANS>
 struct Walk16 {
     static constexpr int kWords = 4 * CHANS;     // filtered words per lane per step (16 pixels)
-    uint32_t soff[CHANS];                        // byte offsets inside the warp tile where this lane stores its chunks
+    uint32_t soff[CHANS];                        // byte offsets inside a tile where this lane's copies land
 
     __device__ __forceinline__ void init(uint32_t lane)
     {
@@ -36,42 +51,49 @@ struct Walk16 {
         }
     }
 
-    // Loads + filters one step; returns the lane's 16 pixels (dw: filtered bytes in memory order) and adds the step's
-    // Adler partials (sum of bytes, position-weighted sum) to sumA / sumB.
-    template <bool kAdler>
-    __device__ __forceinline__ void load_step(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev, uint32_t step, uint32_t bpl,
-                                              uint32_t lane, uint8_t* tile /*this warp's kTileBytes*/, uint32_t (&dw)[kWords],
-                                              uint32_t& sumA, unsigned long long& sumB)
+    // issue the copies of one step into pipeline stage `stage` (0/1) of this warp's tile memory
+    __device__ __forceinline__ void prefetch(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev, uint32_t step, uint32_t bpl,
+                                             uint32_t lane, uint8_t* warp_tiles, uint32_t stage) const
     {
+        uint8_t* tc = warp_tiles + stage * kTileStageBytes;
+        uint8_t* tp = tc + kTileBytes;
         const uint32_t step_base = step * (uint32_t)(kStep16 * CHANS);
 #pragma unroll
         for (int j = 0; j < CHANS; j++) {
             const uint32_t b = step_base + (j * 32u + lane) * 16u;
-            uint4 d = make_uint4(0, 0, 0, 0);
-            if (b < bpl) {
-                const uint4 c = __ldg(reinterpret_cast<const uint4*>(cur + b));
-                if (prev) {
-                    const uint4 p = __ldg(reinterpret_cast<const uint4*>(prev + b));
-                    d.x = vsub4(c.x, p.x); d.y = vsub4(c.y, p.y); d.z = vsub4(c.z, p.z); d.w = vsub4(c.w, p.w);
-                } else d = c;
-                if (kAdler) {
-                    uint32_t t1 = __dp4a(d.x, 0x01010101u, 0u), t2 = __dp4a(d.x, 0x03020100u, 0u);
-                    t1 = __dp4a(d.y, 0x01010101u, t1); t2 = __dp4a(d.y, 0x07060504u, t2);
-                    t1 = __dp4a(d.z, 0x01010101u, t1); t2 = __dp4a(d.z, 0x0B0A0908u, t2);
-                    t1 = __dp4a(d.w, 0x01010101u, t1); t2 = __dp4a(d.w, 0x0F0E0D0Cu, t2);
-                    sumA += t1;
-                    sumB += (unsigned long long)b * t1 + t2;
-                }
-            }
-            *reinterpret_cast<uint4*>(tile + soff[j]) = d;
+            const bool valid = b < bpl;
+            cp_async16(tc + soff[j], cur + (valid ? b : 0u), valid);
+            if (prev) cp_async16(tp + soff[j], prev + (valid ? b : 0u), valid);
         }
-        __syncwarp();
+        cp_async_commit();
+    }
+
+    // read the lane's 16 pixels of a landed stage, apply the Up filter (fpng.cpp:1605-1652), optionally add the Adler
+    // partials (sum of bytes, position-weighted sum) of these 16*CHANS bytes
+    template <bool kAdler>
+    __device__ __forceinline__ void consume(bool have_prev, uint32_t step, uint32_t lane, const uint8_t* warp_tiles, uint32_t stage,
+                                            uint32_t (&dw)[kWords], uint32_t& sumA, unsigned long long& sumB) const
+    {
+        const uint8_t* tc = warp_tiles + stage * kTileStageBytes + lane * kTileLaneBytes;
+        const uint8_t* tp = tc + kTileBytes;
+        const uint32_t lane_base = (step * (uint32_t)kStep16 + lane * (uint32_t)kPix16) * CHANS;     // byte offset of the lane's first byte in the row
 #pragma unroll
         for (int i = 0; i < CHANS; i++) {
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + lane * kTileLaneBytes + i * 16);
-            dw[4 * i] = v.x; dw[4 * i + 1] = v.y; dw[4 * i + 2] = v.z; dw[4 * i + 3] = v.w;
+            uint4 d = *reinterpret_cast<const uint4*>(tc + i * 16);
+            if (have_prev) {
+                const uint4 q = *reinterpret_cast<const uint4*>(tp + i * 16);
+                d.x = vsub4(d.x, q.x); d.y = vsub4(d.y, q.y); d.z = vsub4(d.z, q.z); d.w = vsub4(d.w, q.w);
+            }
+            if (kAdler) {
+                uint32_t t1 = __dp4a(d.x, 0x01010101u, 0u), t2 = __dp4a(d.x, 0x03020100u, 0u);
+                t1 = __dp4a(d.y, 0x01010101u, t1); t2 = __dp4a(d.y, 0x07060504u, t2);
+                t1 = __dp4a(d.z, 0x01010101u, t1); t2 = __dp4a(d.z, 0x0B0A0908u, t2);
+                t1 = __dp4a(d.w, 0x01010101u, t1); t2 = __dp4a(d.w, 0x0F0E0D0Cu, t2);
+                sumA += t1;
+                sumB += (unsigned long long)(lane_base + 16u * i) * t1 + t2;
+            }
+            dw[4 * i] = d.x; dw[4 * i + 1] = d.y; dw[4 * i + 2] = d.z; dw[4 * i + 3] = d.w;
         }
-        __syncwarp();
     }
 
     __device__ __forceinline__ static void pixels(const uint32_t (&dw)[kWords], uint32_t (&px)[16])
