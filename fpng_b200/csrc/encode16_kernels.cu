@@ -248,15 +248,32 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         // staging bit 0 corresponds to row bit (flushed_bits - g31); the filter literal sits at row bit 0
         if (step == 0 && lane == 0) { bs.begin(g31); bs.put(fcode & 0xFFFFu, fcode >> 16); }
         else bs.begin(g31 + my_ofs - flushed_bits);
+        // The 16 pixels are emitted in 4 groups of 4 by a ROLLED loop (the group's pixels are selected from registers):
+        // a fully unrolled body is ~80 KB of SASS and stalls on instruction fetch (ncu: no_instruction dominated).
         uint32_t r = t.run;
+        const bool all_lit = __all_sync(kFullMask, t.litm == 0xFFFFu);
+        if (all_lit && r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }   // only lane 0 can carry one in
+#pragma unroll 1
+        for (uint32_t g = 0; g < 4; g++) {
+            uint32_t q[4];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if ((uint32_t)k < t.nvp) {
-                if (t.eqm & (1u << k)) {
-                    if (++r == M) { const uint32_t m = s_match[M]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
-                } else {
-                    if (r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
-                    put_literal16<CHANS>(bs, s_lit, px[k]);
+            for (int j = 0; j < 4; j++) q[j] = g == 0 ? px[j] : (g == 1 ? px[4 + j] : (g == 2 ? px[8 + j] : px[12 + j]));
+            if (all_lit) {
+                // warp-uniform fast path (noisy rows): straight-line literal emission
+#pragma unroll
+                for (int j = 0; j < 4; j++) put_literal16<CHANS>(bs, s_lit, q[j]);
+            } else {
+                const uint32_t e4 = t.eqm >> (4u * g);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (4u * g + j < t.nvp) {
+                        if (e4 & (1u << j)) {
+                            if (++r == M) { const uint32_t m = s_match[M]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
+                        } else {
+                            if (r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
+                            put_literal16<CHANS>(bs, s_lit, q[j]);
+                        }
+                    }
                 }
             }
         }
