@@ -331,9 +331,21 @@ def run_ours(args, wl):
     algo = {"hist": in_bytes, "huffman": 0, "scan": in_bytes, "offsets": 0, "pack": in_bytes + out_bytes, "adler": 0, "crc": out_bytes}
     dominant = max(kern, key=lambda k: kern[k])
 
+    # DRAM traffic per launch from the committed `ncu --set full` capture of the same workload (profiles/traffic.json,
+    # written by profiles/extract_ncu.py), scaled from the capture's image count to this launch; null when no capture exists
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic_db = json.load(f)
+    except Exception:
+        traffic_db = {}
+
+    def traffic_of(k):
+        t = traffic_db.get(f"{args.workload}/{args.kind}/{k}")
+        return t["dram_bytes_per_launch"] * n / t["images_in_capture"] if t else None
+
     def roof(k):
         gbs = algo[k] / 1e9 / (kern[k] / 1e3) if kern[k] > 0 else 0.0
-        return {"kernel": k, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+        return {"kernel": k, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic_of(k),
                 "ms_per_launch": kern[k], "algorithmic_bytes_per_launch": algo[k], "peak_source": peak_src}
 
     line = {

@@ -137,30 +137,35 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
 // only this lane's bits), its first word through a side slot and its last partial word with atomicOr.
 // ------------------------------------------------------------------------------------------------
 struct BitStager16 {
-    uint32_t* stage;            // warp staging words (zero outside the live range)
-    uint32_t* side;             // this lane's private slot for its first (shared) word
-    unsigned long long acc;
-    uint32_t nacc, wpos, firstw;
-    __device__ __forceinline__ void begin(uint32_t bitpos) { acc = 0; nacc = bitpos & 31u; wpos = firstw = bitpos >> 5; }
-    // append `len` (<= 32) bits; nacc < 32 on entry.  acc has no bits at or above nacc, so add == or and the shift can
-    // be done as a widening multiply-add on the FMA pipe.
+    uint32_t cur, n;            // word being filled (n < 32 valid bits)
+    uint32_t* dst;              // where `cur` goes once complete: the side slot for the lane's first word, staging afterwards
+    uint32_t* nxt;              // staging address of the word after `cur`
+    uint32_t* first_stage;      // staging address of the lane's first word
+    uint32_t* side;
+    __device__ __forceinline__ void begin(uint32_t* stage, uint32_t* side_slot, uint32_t bitpos)
+    {
+        cur = 0; n = bitpos & 31u; side = side_slot;
+        first_stage = stage + (bitpos >> 5); dst = side_slot; nxt = first_stage + 1;
+    }
+    // append `len` (<= 32 - with code < 2^len) bits
     __device__ __forceinline__ void put(uint32_t code, uint32_t len)
     {
-        acc = (unsigned long long)code * (unsigned long long)(1u << nacc) + acc;
-        nacc += len;
-        const uint32_t f = nacc >> 5;                                   // 1 when the low word is complete
-        uint32_t* dst = (wpos == firstw) ? side : stage + wpos;
-        if (f) *dst = (uint32_t)acc;
-        acc >>= (f << 5);
-        nacc &= 31u;
-        wpos += f;
+        const uint32_t lo = cur | (code << n);
+        const uint32_t hi = __funnelshift_l(code, 0u, n);               // bits that spill into the next word
+        const uint32_t n2 = n + len;
+        const bool f = n2 >= 32u;
+        if (f) *dst = lo;                                                // complete words hold only this lane's bits (or go to the side slot)
+        cur = f ? hi : lo;
+        n = n2 & 31u;
+        dst = f ? nxt : dst;
+        nxt += f ? 1 : 0;
     }
     __device__ __forceinline__ void end()
     {
-        if (wpos == firstw) { if ((uint32_t)acc) atomicOr(&stage[firstw], (uint32_t)acc); }       // everything fits in the first word
+        if (dst == side) { if (cur) atomicOr(first_stage, cur); }        // everything fits in the first word
         else {
-            atomicOr(&stage[firstw], *side);
-            if ((uint32_t)acc) atomicOr(&stage[wpos], (uint32_t)acc);
+            atomicOr(first_stage, *side);
+            if (cur) atomicOr(dst, cur);
         }
     }
 };
@@ -244,10 +249,11 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         const uint32_t my_ofs = lane_ofs[step * 32u + lane];
         const uint32_t step_end = (step + 1 < nsteps) ? lane_ofs[(step + 1) * 32u] : row_total;   // row bits after this step
 
-        BitStager16 bs; bs.stage = stage; bs.side = s_side_all + warp * 32 + lane;
+        BitStager16 bs;
+        uint32_t* side_slot = s_side_all + warp * 32 + lane;
         // staging bit 0 corresponds to row bit (flushed_bits - g31); the filter literal sits at row bit 0
-        if (step == 0 && lane == 0) { bs.begin(g31); bs.put(fcode & 0xFFFFu, fcode >> 16); }
-        else bs.begin(g31 + my_ofs - flushed_bits);
+        if (step == 0 && lane == 0) { bs.begin(stage, side_slot, g31); bs.put(fcode & 0xFFFFu, fcode >> 16); }
+        else bs.begin(stage, side_slot, g31 + my_ofs - flushed_bits);
         // The 16 pixels are emitted in 4 groups of 4 by a ROLLED loop (the group's pixels are selected from registers):
         // a fully unrolled body is ~80 KB of SASS and stalls on instruction fetch (ncu: no_instruction dominated).
         uint32_t r = t.run;
