@@ -122,44 +122,11 @@ __device__ __forceinline__ uint32_t mul_level(const uint32_t (*t)[16], uint32_t 
     return r;
 }
 
-// One thread owns one 128-byte chunk: it loads the chunk straight into registers (8 x 128-bit loads; the 32 lanes of a
-// warp touch 32 different 128-byte lines, every byte of which is used), runs the slice-by-4 CRC over the 32 words, and the
-// CTA combines the 256 chunk CRCs of a tile with the multiply-by-x^(8*len) tree.  The next tile's loads are issued before
-// the current tile is processed (software pipelining); no shared-memory staging of the data.
-// first / last tile of a message only: 16 bytes with conditioning (kept out of line: it is rare and large)
-__device__ __noinline__ uint4 crc_load_conditioned(const uint8_t* __restrict__ file, uint32_t wo, uint32_t start, uint32_t L, uint32_t init)
-{
-    uint4 t = make_uint4(0, 0, 0, 0);
-    if (wo < L) t = __ldg(reinterpret_cast<const uint4*>(file + wo));
-    t.x = condition_word(t.x, wo, start, L, init);
-    t.y = condition_word(t.y, wo + 4u, start, L, init);
-    t.z = condition_word(t.z, wo + 8u, start, L, init);
-    t.w = condition_word(t.w, wo + 12u, start, L, init);
-    return t;
-}
-
-__device__ __forceinline__ void crc_load_chunk(const uint8_t* __restrict__ file, uint32_t chunk_ofs, uint32_t start, uint32_t L, uint32_t init,
-                                               bool interior, uint4 (&v)[8])
-{
-    if (interior) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __ldg(reinterpret_cast<const uint4*>(file + chunk_ofs) + i);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = crc_load_conditioned(file, chunk_ofs + 16u * i, start, L, init);
-    }
-}
-
-__device__ __forceinline__ uint32_t crc_word(const uint32_t (*tab)[256], uint32_t crc, uint32_t w)
-{
-    const uint32_t x = w ^ crc;
-    return tab[3][x & 0xFF] ^ tab[2][(x >> 8) & 0xFF] ^ tab[1][(x >> 16) & 0xFF] ^ tab[0][x >> 24];
-}
-
 __global__ void __launch_bounds__(kCrcThreads) idat_crc_kernel(CrcParams p)
 {
     __shared__ uint32_t s_tab[4][256];
     __shared__ uint32_t s_mul[8][8][16];
+    __shared__ uint32_t s_data[kCrcThreads * (kChunkWords + 1)];
     __shared__ uint32_t s_warp[kCrcThreads / 32];
 
     const uint32_t img = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -176,22 +143,35 @@ __global__ void __launch_bounds__(kCrcThreads) idat_crc_kernel(CrcParams p)
     const uint32_t t0 = b * kTilesPerCta, t1 = min(t0 + kTilesPerCta, ntiles);
     uint32_t acc = 0;                                                  // Horner accumulator (thread 0)
 
-    uint4 cur[8], nxt[8];
-    {
-        const uint32_t tile_ofs = t0 * kTileBytes;
-        crc_load_chunk(file, tile_ofs + tid * 128u, start, L, init, tile_ofs >= start + 4u && tile_ofs + kTileBytes <= L, cur);
-    }
-    __syncthreads();
     for (uint32_t tile = t0; tile < t1; tile++) {
-        if (tile + 1 < t1) {
-            const uint32_t tile_ofs = (tile + 1) * kTileBytes;
-            crc_load_chunk(file, tile_ofs + tid * 128u, start, L, init, tile_ofs >= start + 4u && tile_ofs + kTileBytes <= L, nxt);
+        const uint32_t tile_ofs = tile * kTileBytes;
+        __syncthreads();
+        // coalesced 16-byte loads -> padded shared layout (chunk c at words [33c, 33c+32))
+        // tiles strictly inside the message need no conditioning (only the first and last tile of a file do)
+        const bool interior = tile_ofs >= start + 4u && tile_ofs + kTileBytes <= L;
+        for (uint32_t g = tid; g < kTileWords / 4; g += blockDim.x) {
+            const uint32_t wo = tile_ofs + g * 16u;
+            const uint32_t wi = g * 4u, base = (wi / kChunkWords) * (kChunkWords + 1) + (wi % kChunkWords);
+            if (interior) {
+                const uint4 v = *reinterpret_cast<const uint4*>(file + wo);
+                s_data[base + 0] = v.x; s_data[base + 1] = v.y; s_data[base + 2] = v.z; s_data[base + 3] = v.w;
+            } else {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (wo < L) v = *reinterpret_cast<const uint4*>(file + wo);
+                s_data[base + 0] = condition_word(v.x, wo, start, L, init);
+                s_data[base + 1] = condition_word(v.y, wo + 4u, start, L, init);
+                s_data[base + 2] = condition_word(v.z, wo + 8u, start, L, init);
+                s_data[base + 3] = condition_word(v.w, wo + 12u, start, L, init);
+            }
         }
+        __syncthreads();
+
         uint32_t crc = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            crc = crc_word(s_tab, crc, cur[i].x); crc = crc_word(s_tab, crc, cur[i].y);
-            crc = crc_word(s_tab, crc, cur[i].z); crc = crc_word(s_tab, crc, cur[i].w);
+        const uint32_t* chunk = s_data + tid * (kChunkWords + 1);
+#pragma unroll 4
+        for (int j = 0; j < kChunkWords; j++) {
+            const uint32_t x = chunk[j] ^ crc;
+            crc = s_tab[3][x & 0xFF] ^ s_tab[2][(x >> 8) & 0xFF] ^ s_tab[1][(x >> 16) & 0xFF] ^ s_tab[0][x >> 24];
         }
         // tree combine: chunk i must be multiplied by x^(8*128*(255-i))
 #pragma unroll
@@ -212,9 +192,6 @@ __global__ void __launch_bounds__(kCrcThreads) idat_crc_kernel(CrcParams p)
             }
             if (lane == 0) acc = gf2_mulmod(acc, c_tile) ^ v;
         }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 8; i++) cur[i] = nxt[i];
     }
 
     if (tid == 0) {
