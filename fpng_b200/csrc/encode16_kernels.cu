@@ -132,6 +132,86 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1-hist (v2): 288-bin literal/length histogram of 2-pass mode (fpng.cpp:1021-1084, 1299-1363) on the 16-pixel walker.
+// Warp-private shared-memory histograms (no inter-warp contention), merged per CTA, then added to the image's bins.
+// ------------------------------------------------------------------------------------------------
+template <int CHANS>
+__global__ void __launch_bounds__(32 * kScan16Rows) row_hist16_kernel(ScanParams p)
+{
+    constexpr uint32_t M = max_match_pixels(CHANS);
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    uint32_t* s_hist_all = reinterpret_cast<uint32_t*>(dyn_smem + kScan16Rows * kTileWarpBytes);   // [warps][288]
+    __shared__ uint16_t s_lensym[88];
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t img = blockIdx.y;
+    const uint32_t y = blockIdx.x * kScan16Rows + warp;
+    for (uint32_t i = threadIdx.x; i < kScan16Rows * 288; i += blockDim.x) s_hist_all[i] = 0u;
+    if (threadIdx.x >= 1 && threadIdx.x <= M) { uint32_t sy, xb, xv; deflate_len_code(threadIdx.x * CHANS, sy, xb, xv); s_lensym[threadIdx.x] = (uint16_t)sy; }
+    __syncthreads();
+    uint32_t* hist = s_hist_all + warp * 288;
+
+    if (y < p.h) {
+        const uint32_t w = p.w, bpl = w * CHANS;
+        const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
+        const uint8_t* prev = y ? cur - bpl : nullptr;
+        const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
+        uint8_t* tiles = dyn_smem + warp * kTileWarpBytes;
+        Walk16<CHANS> wk; wk.init(lane);
+        RowCarry carry = {0u, 0u};
+        uint32_t dummyA = 0; unsigned long long dummyB = 0;
+        if (lane == 0) atomicAdd(&hist[y ? 2 : 0], 1u);               // the filter literal
+        wk.prefetch(cur, prev, 0, bpl, lane, tiles, 0);
+        for (uint32_t step = 0; step < nsteps; step++) {
+            uint32_t dw[Walk16<CHANS>::kWords], px[16];
+            cp_async_wait<0>();
+            __syncwarp();
+            wk.template consume<false>(prev != nullptr, step, lane, tiles, 0, dw, dummyA, dummyB);
+            __syncwarp();
+            if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles, 0);
+            Walk16<CHANS>::pixels(dw, px);
+            const uint32_t p0 = step * kStep16 + lane * kPix16;
+            const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
+            if (__any_sync(kFullMask, t.litm != 0)) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (t.litm & (1u << k)) {
+                        atomicAdd(&hist[px[k] & 0xFFu], 1u);
+                        atomicAdd(&hist[byte1(px[k])], 1u);
+                        if (CHANS == 4) { atomicAdd(&hist[byte2(px[k])], 1u); atomicAdd(&hist[px[k] >> 24], 1u); }
+                        else atomicAdd(&hist[px[k] >> 16], 1u);
+                    }
+                }
+            }
+            uint32_t r = t.run, pos = 0;
+            const uint32_t nvp = t.nvp;
+            if (t.eqm | r) {
+                while (pos < nvp) {
+                    const uint32_t m = t.eqm >> pos;
+                    const uint32_t ones = min((uint32_t)__ffs((int)~m) - 1u, nvp - pos);
+                    if (ones) {
+                        r += ones; pos += ones;
+                        if (r >= M) { atomicAdd(&hist[s_lensym[M]], 1u); r -= M; }
+                        if (pos >= nvp) break;
+                    }
+                    if (r) { atomicAdd(&hist[s_lensym[r]], 1u); r = 0; }
+                    const uint32_t mz = t.eqm >> pos;
+                    pos += mz ? (uint32_t)__ffs((int)mz) - 1u : 32u;
+                }
+            }
+            if (t.last && r) atomicAdd(&hist[s_lensym[r]], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 288; i += blockDim.x) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int wq = 0; wq < kScan16Rows; wq++) v += s_hist_all[wq * 288 + i];
+        if (v) atomicAdd(&p.hist[(size_t)img * 288 + i], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3 (v2): pack.  Every lane knows where its 16 pixels' tokens start (lane_ofs from the scan kernel), so it emits its
 // codes with a 64-bit accumulator straight into the warp's staging words: complete words with plain stores (they hold
 // only this lane's bits), its first word through a side slot and its last partial word with atomicOr.
@@ -266,8 +346,20 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
             for (int j = 0; j < 4; j++) q[j] = g == 0 ? px[j] : (g == 1 ? px[4 + j] : (g == 2 ? px[8 + j] : px[12 + j]));
             if (all_lit) {
                 // warp-uniform fast path (noisy rows): straight-line literal emission
+                if (CHANS == 3) {
+                    // 12 codes of 4 RGB pixels, appended two at a time (<= 24 bits per put): 6 puts instead of 8
+                    uint32_t e[12];
 #pragma unroll
-                for (int j = 0; j < 4; j++) put_literal16<CHANS>(bs, s_lit, q[j]);
+                    for (int j = 0; j < 4; j++) { e[3 * j] = s_lit[q[j] & 0xFFu]; e[3 * j + 1] = s_lit[byte1(q[j])]; e[3 * j + 2] = s_lit[q[j] >> 16]; }
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        const uint32_t a = e[2 * j], b = e[2 * j + 1], la = a >> 16;
+                        bs.put((a & 0xFFFFu) | ((b & 0xFFFFu) << la), la + (b >> 16));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) put_literal16<CHANS>(bs, s_lit, q[j]);
+                }
             } else {
                 const uint32_t e4 = t.eqm >> (4u * g);
 #pragma unroll
@@ -329,6 +421,14 @@ void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t
     dim3 grid((p.h + kScan16Rows - 1) / kScan16Rows, n);
     if (chans == 4) { FPNGB_SET_SMEM(row_scan16_kernel<4>, kScan16Smem); row_scan16_kernel<4><<<grid, 32 * kScan16Rows, kScan16Smem, s>>>(p); }
     else { FPNGB_SET_SMEM(row_scan16_kernel<3>, kScan16Smem); row_scan16_kernel<3><<<grid, 32 * kScan16Rows, kScan16Smem, s>>>(p); }
+}
+
+constexpr size_t kHist16Smem = kScan16Rows * kTileWarpBytes + kScan16Rows * 288 * 4;
+void launch_hist16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
+{
+    dim3 grid((p.h + kScan16Rows - 1) / kScan16Rows, n);
+    if (chans == 4) { FPNGB_SET_SMEM(row_hist16_kernel<4>, kHist16Smem); row_hist16_kernel<4><<<grid, 32 * kScan16Rows, kHist16Smem, s>>>(p); }
+    else { FPNGB_SET_SMEM(row_hist16_kernel<3>, kHist16Smem); row_hist16_kernel<3><<<grid, 32 * kScan16Rows, kHist16Smem, s>>>(p); }
 }
 
 void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s)

@@ -250,7 +250,7 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     ProfSet* ps = prof_begin(s);
     if (two_pass) {
         FPNGB_CUDA_OK(cudaMemsetAsync(ws.hist, 0, (size_t)n * 288 * 4, s));
-        launch_scan(sp, n, chans, mode, true, s);
+        if (v2) launch_hist16(sp, n, chans, s); else launch_scan(sp, n, chans, mode, true, s);
         prof_mark(ps, kProfHist, s);
         HuffParams hp{ws.hist, ws.books, chans};
         launch_huffman_build(hp, n, s);

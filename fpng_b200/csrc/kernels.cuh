@@ -66,6 +66,7 @@ struct HuffParams {
 void launch_scan(const ScanParams& p, uint32_t n, uint32_t chans, int mode, bool hist, cudaStream_t s);
 bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t chans);
 void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s);
+void launch_hist16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s);
 void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s);
 void launch_offsets(const OffsetsParams& p, uint32_t n, cudaStream_t s);
 void launch_pack(const PackParams& p, uint32_t n, uint32_t chans, int mode, cudaStream_t s);
