@@ -79,6 +79,7 @@ static int decode_batch_locked(const uint8_t* d_files, size_t file_stride, const
     const size_t o_subs = o; o = align_up(o + (size_t)n * subs_per_file * sizeof(SubInfo), 256);
     const size_t o_delta = o; o = align_up(o + (size_t)n * pitch * h + 64, 256);
     int rc = g_dec_ws.reserve(o); if (rc) return rc;
+    rc = context().ws_acquire(s); if (rc) return rc;
     g_dec_pin.pinned = true;
     rc = g_dec_pin.reserve((size_t)n * sizeof(FileDesc)); if (rc) return rc;
     // the pinned staging buffer may still be in flight from the previous call on another stream: wait for it
@@ -96,7 +97,7 @@ static int decode_batch_locked(const uint8_t* d_files, size_t file_stride, const
     launch_decode(p, n, desired, s);
     count_launch(8);
     FPNGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return context().ws_release(s);
 }
 
 }  // namespace fpngb

@@ -91,14 +91,15 @@ __device__ static bool build_lut_warp(const uint8_t* sizes, uint32_t nsyms, uint
     const uint32_t lut_size = 1u << lut_bits;
     for (uint32_t i = lane; i < lut_size; i += 32) lut[i] = 0;
     __syncwarp();
-    if (lane == 0) {
-        // serial code assignment (ascending symbol order), parallel replication is not worth it at <= 288 symbols
-        for (uint32_t i = 0; i < nsyms; i++) {
-            const uint32_t l = sizes[i];
-            if (!l) continue;
-            const uint32_t code = __brev(s_next[l]++) >> (32 - l);
-            if (l <= lut_bits) for (uint32_t c = code; c < lut_size; c += 1u << l) lut[c] = (uint16_t)(i | (l << 9));
-        }
+    // canonical code of symbol i = first_code[len] + (number of earlier symbols of the same length); symbols are spread
+    // over the lanes, each lane ranks and replicates its own
+    for (uint32_t i = lane; i < nsyms; i += 32) {
+        const uint32_t l = sizes[i];
+        if (!l || l > lut_bits) continue;
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < i; j++) rank += sizes[j] == l;
+        const uint32_t code = __brev(s_next[l] + rank) >> (32 - l);
+        for (uint32_t c = code; c < lut_size; c += 1u << l) lut[c] = (uint16_t)(i | (l << 9));
     }
     __syncwarp();
     return true;

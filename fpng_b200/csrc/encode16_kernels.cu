@@ -337,15 +337,16 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         // The 16 pixels are emitted in 4 groups of 4 by a ROLLED loop (the group's pixels are selected from registers):
         // a fully unrolled body is ~80 KB of SASS and stalls on instruction fetch (ncu: no_instruction dominated).
         uint32_t r = t.run;
-        const bool all_lit = __all_sync(kFullMask, t.litm == 0xFFFFu);
-        if (all_lit && r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }   // only lane 0 can carry one in
 #pragma unroll 1
         for (uint32_t g = 0; g < 4; g++) {
             uint32_t q[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) q[j] = g == 0 ? px[j] : (g == 1 ? px[4 + j] : (g == 2 ? px[8 + j] : px[12 + j]));
+            // warp-uniform per group: all 128 pixels of this group (4 per lane) are literals
+            const bool all_lit = __all_sync(kFullMask, ((t.litm >> (4u * g)) & 15u) == 15u);
             if (all_lit) {
-                // warp-uniform fast path (noisy rows): straight-line literal emission
+                // fast path (noisy rows): flush a match still pending from the previous group, then straight-line literals
+                if (r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
                 if (CHANS == 3) {
                     // 12 codes of 4 RGB pixels, appended two at a time (<= 24 bits per put): 6 puts instead of 8
                     uint32_t e[12];

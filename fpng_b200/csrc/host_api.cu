@@ -232,6 +232,8 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     Workspace ws;
     int rc = carve_workspace(c, n, h, w, two_pass, ws);
     if (rc) return rc;
+    rc = c.ws_acquire(s);
+    if (rc) return rc;
     const int mode = pick_load_mode(d_pixels, image_stride, w, chans);
     // second-generation kernels (16 pixels per lane, coalesced 128-bit loads) whenever every scanline is 16-byte aligned;
     // FPNGB_FORCE_GENERIC=1 keeps the generic kernels (tests compare both)
@@ -284,7 +286,7 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     prof_mark(ps, kProfCrc, s);
     count_launch(5);
     FPNGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return c.ws_release(s);
 }
 
 }  // namespace fpngb

@@ -29,6 +29,23 @@ struct Context {
     Buffer pin_small;                             // pinned scratch for sizes / status words
     std::mutex mu;                                // the *_host entry points and the workspace are serialised
     bool ready = false;
+    // The workspaces are shared by consecutive batch calls: work enqueued on a different stream than the previous call
+    // first waits (on the device) for that call's kernels.
+    cudaEvent_t ws_done = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_busy = false;
+    int ws_acquire(cudaStream_t s)
+    {
+        if (!ws_done) FPNGB_CUDA_OK(cudaEventCreateWithFlags(&ws_done, cudaEventDisableTiming));
+        if (ws_busy && ws_stream != s) FPNGB_CUDA_OK(cudaStreamWaitEvent(s, ws_done, 0));
+        return 0;
+    }
+    int ws_release(cudaStream_t s)
+    {
+        FPNGB_CUDA_OK(cudaEventRecord(ws_done, s));
+        ws_stream = s; ws_busy = true;
+        return 0;
+    }
 };
 
 

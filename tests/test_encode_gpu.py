@@ -176,3 +176,42 @@ sys.exit(1 if bad else 0)
     env = dict(os.environ, FPNGB_FORCE_GENERIC="1")
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_concurrent_host_threads_and_streams(gpu, oracle):
+    """Entry points are callable from several host threads (serialised internally) and on different CUDA streams."""
+    import threading
+    import torch
+    imgs = {i: imagegen.make("g1", 320 + 16 * i, 40 + i, 3 + (i & 1), i) for i in range(8)}
+    exp = {i: oracle.encode(im, im.shape[1], im.shape[0], im.shape[2], 0) for i, im in imgs.items()}
+    errs = []
+
+    def worker(i):
+        for _ in range(5):
+            ok, png = gpu.fpng_encode_image_to_memory(imgs[i], imgs[i].shape[1], imgs[i].shape[0], imgs[i].shape[2], 0)
+            if not ok or png != exp[i]:
+                errs.append(i)
+            st, px, *_ = gpu.fpng_decode_memory(png, imgs[i].shape[2])
+            if st != 0 or not np.array_equal(px, imgs[i].reshape(-1)):
+                errs.append(100 + i)
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    # two streams, back-to-back batch calls sharing the workspace
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    a = torch.from_numpy(np.stack([imagegen.make("g1", 512, 64, 4, i) for i in range(6)])).cuda()
+    b = torch.from_numpy(np.stack([imagegen.make("g0", 512, 64, 4, i) for i in range(6)])).cuda()
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(4):
+        oa, sa = gpu.encode_batch_device(a, 0, stream=s1.cuda_stream)
+        ob, sb = gpu.encode_batch_device(b, 0, stream=s2.cuda_stream)
+        outs.append((oa, sa, ob, sb))
+    torch.cuda.synchronize()
+    for oa, sa, ob, sb in outs:
+        for t, o, s in ((a, oa, sa), (b, ob, sb)):
+            sz = s.cpu().numpy().astype(np.int64)
+            for i in range(6):
+                assert bytes(o[i, : sz[i]].cpu().numpy()) == oracle.encode(t[i].cpu().numpy(), 512, 64, 4, 0)
