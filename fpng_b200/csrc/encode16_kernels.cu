@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
 {
     constexpr uint32_t M = max_match_pixels(CHANS);
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    uint8_t* s_lit = dyn_smem + kScan16Rows * kTileWarpBytes;
+    uint8_t* s_lit = dyn_smem + kScan16Rows * Walk16<CHANS>::kWarpBytes;
     uint8_t* s_match = s_lit + 256;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -47,23 +47,20 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
     const uint8_t* prev = y ? cur - bpl : nullptr;
     const uint32_t filt = y ? 2u : 0u;
     const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
-    uint8_t* tiles = dyn_smem + warp * kTileWarpBytes;
+    uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
     uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
 
-    Walk16<CHANS> wk; wk.init(lane);
+    Walk16<CHANS> wk; wk.init(lane, tiles);
     RowCarry carry = {0u, 0u};
     uint32_t row_run = s_lit[filt];              // bits of the row emitted before the current step (filter literal first)
     uint32_t sumA = 0, last_unit = 0;
     unsigned long long sumB = 0;
 
-    wk.prefetch(cur, prev, 0, bpl, lane, tiles, 0);
+    wk.prefetch(cur, prev, 0, bpl, lane, tiles);
     for (uint32_t step = 0; step < nsteps; step++) {
         uint32_t dw[Walk16<CHANS>::kWords], px[16];
-        cp_async_wait<0>();
-        __syncwarp();
-        wk.template consume<true>(prev != nullptr, step, lane, tiles, 0, dw, sumA, sumB);
-        __syncwarp();
-        if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles, 0);      // lands while this step is processed
+        wk.template consume<true>(prev != nullptr, step, bpl, lane, tiles, dw, sumA, sumB);
+        if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);         // lands while this step is processed
         Walk16<CHANS>::pixels(dw, px);
         const uint32_t p0 = step * kStep16 + lane * kPix16;
         const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
@@ -140,7 +137,7 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_hist16_kernel(ScanParams
 {
     constexpr uint32_t M = max_match_pixels(CHANS);
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    uint32_t* s_hist_all = reinterpret_cast<uint32_t*>(dyn_smem + kScan16Rows * kTileWarpBytes);   // [warps][288]
+    uint32_t* s_hist_all = reinterpret_cast<uint32_t*>(dyn_smem + kScan16Rows * Walk16<CHANS>::kWarpBytes);   // [warps][288]
     __shared__ uint16_t s_lensym[88];
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,19 +153,16 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_hist16_kernel(ScanParams
         const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
         const uint8_t* prev = y ? cur - bpl : nullptr;
         const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
-        uint8_t* tiles = dyn_smem + warp * kTileWarpBytes;
-        Walk16<CHANS> wk; wk.init(lane);
+        uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
+        Walk16<CHANS> wk; wk.init(lane, tiles);
         RowCarry carry = {0u, 0u};
         uint32_t dummyA = 0; unsigned long long dummyB = 0;
         if (lane == 0) atomicAdd(&hist[y ? 2 : 0], 1u);               // the filter literal
-        wk.prefetch(cur, prev, 0, bpl, lane, tiles, 0);
+        wk.prefetch(cur, prev, 0, bpl, lane, tiles);
         for (uint32_t step = 0; step < nsteps; step++) {
             uint32_t dw[Walk16<CHANS>::kWords], px[16];
-            cp_async_wait<0>();
-            __syncwarp();
-            wk.template consume<false>(prev != nullptr, step, lane, tiles, 0, dw, dummyA, dummyB);
-            __syncwarp();
-            if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles, 0);
+            wk.template consume<false>(prev != nullptr, step, bpl, lane, tiles, dw, dummyA, dummyB);
+            if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);
             Walk16<CHANS>::pixels(dw, px);
             const uint32_t p0 = step * kStep16 + lane * kPix16;
             const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
@@ -272,7 +266,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
 {
     constexpr uint32_t M = max_match_pixels(CHANS);
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    uint32_t* s_lit = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * kTileWarpBytes);
+    uint32_t* s_lit = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * Walk16<CHANS>::kWarpBytes);
     uint32_t* s_match = s_lit + 256;
     uint32_t* s_stage_all = s_match + 88;
     uint32_t* s_side_all = s_stage_all + kPack16Rows * kStage16Words;
@@ -301,7 +295,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     const uint8_t* prev = y ? cur - bpl : nullptr;
     uint32_t* file_words = reinterpret_cast<uint32_t*>(p.out + (size_t)img * p.out_stride);
     uint32_t* stage = s_stage_all + warp * kStage16Words;
-    uint8_t* tiles = dyn_smem + warp * kTileWarpBytes;
+    uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
     const uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
     const uint32_t row_total = p.row_bits[(size_t)img * p.h + y];
     const unsigned long long G = p.row_ofs[(size_t)img * p.h + y];
@@ -312,17 +306,14 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
     const uint32_t fcode = s_lit[y ? 2 : 0];
 
-    Walk16<CHANS> wk; wk.init(lane);
+    Walk16<CHANS> wk; wk.init(lane, tiles);
     RowCarry carry = {0u, 0u};
     uint32_t dummyA = 0; unsigned long long dummyB = 0;
-    wk.prefetch(cur, prev, 0, bpl, lane, tiles, 0);
+    wk.prefetch(cur, prev, 0, bpl, lane, tiles);
     for (uint32_t step = 0; step < nsteps; step++) {
         uint32_t dw[Walk16<CHANS>::kWords], px[16];
-        cp_async_wait<0>();
-        __syncwarp();
-        wk.template consume<false>(prev != nullptr, step, lane, tiles, 0, dw, dummyA, dummyB);
-        __syncwarp();
-        if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles, 0);      // lands while this step is emitted
+        wk.template consume<false>(prev != nullptr, step, bpl, lane, tiles, dw, dummyA, dummyB);
+        if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);         // lands while this step is emitted
         Walk16<CHANS>::pixels(dw, px);
         const uint32_t p0 = step * kStep16 + lane * kPix16;
         const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
@@ -410,8 +401,8 @@ bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t
     return ((uintptr_t)base % 16 == 0) && (image_stride % 16 == 0) && (bpl % 16 == 0);
 }
 
-constexpr size_t kScan16Smem = kScan16Rows * kTileWarpBytes + 256 + 96;
-constexpr size_t kPack16Smem = kPack16Rows * kTileWarpBytes + (256 + 88 + kPack16Rows * kStage16Words + kPack16Rows * 32) * 4;
+template <int CHANS> constexpr size_t scan16_smem() { return kScan16Rows * Walk16<CHANS>::kWarpBytes + 256 + 96; }
+template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk16<CHANS>::kWarpBytes + (256 + 88 + kPack16Rows * kStage16Words + kPack16Rows * 32) * 4; }
 
 // opt in to > 48 KiB of dynamic shared memory (per kernel instantiation, once per process)
 #define FPNGB_SET_SMEM(kernel, bytes) do { static bool done_ = false; \
@@ -420,23 +411,23 @@ constexpr size_t kPack16Smem = kPack16Rows * kTileWarpBytes + (256 + 88 + kPack1
 void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
     dim3 grid((p.h + kScan16Rows - 1) / kScan16Rows, n);
-    if (chans == 4) { FPNGB_SET_SMEM(row_scan16_kernel<4>, kScan16Smem); row_scan16_kernel<4><<<grid, 32 * kScan16Rows, kScan16Smem, s>>>(p); }
-    else { FPNGB_SET_SMEM(row_scan16_kernel<3>, kScan16Smem); row_scan16_kernel<3><<<grid, 32 * kScan16Rows, kScan16Smem, s>>>(p); }
+    if (chans == 4) { FPNGB_SET_SMEM(row_scan16_kernel<4>, scan16_smem<4>()); row_scan16_kernel<4><<<grid, 32 * kScan16Rows, scan16_smem<4>(), s>>>(p); }
+    else { FPNGB_SET_SMEM(row_scan16_kernel<3>, scan16_smem<3>()); row_scan16_kernel<3><<<grid, 32 * kScan16Rows, scan16_smem<3>(), s>>>(p); }
 }
 
-constexpr size_t kHist16Smem = kScan16Rows * kTileWarpBytes + kScan16Rows * 288 * 4;
+template <int CHANS> constexpr size_t hist16_smem() { return kScan16Rows * Walk16<CHANS>::kWarpBytes + kScan16Rows * 288 * 4; }
 void launch_hist16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
     dim3 grid((p.h + kScan16Rows - 1) / kScan16Rows, n);
-    if (chans == 4) { FPNGB_SET_SMEM(row_hist16_kernel<4>, kHist16Smem); row_hist16_kernel<4><<<grid, 32 * kScan16Rows, kHist16Smem, s>>>(p); }
-    else { FPNGB_SET_SMEM(row_hist16_kernel<3>, kHist16Smem); row_hist16_kernel<3><<<grid, 32 * kScan16Rows, kHist16Smem, s>>>(p); }
+    if (chans == 4) { FPNGB_SET_SMEM(row_hist16_kernel<4>, hist16_smem<4>()); row_hist16_kernel<4><<<grid, 32 * kScan16Rows, hist16_smem<4>(), s>>>(p); }
+    else { FPNGB_SET_SMEM(row_hist16_kernel<3>, hist16_smem<3>()); row_hist16_kernel<3><<<grid, 32 * kScan16Rows, hist16_smem<3>(), s>>>(p); }
 }
 
 void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
     dim3 grid((p.h + kPack16Rows - 1) / kPack16Rows, n);
-    if (chans == 4) { FPNGB_SET_SMEM(pack_rows16_kernel<4>, kPack16Smem); pack_rows16_kernel<4><<<grid, 32 * kPack16Rows, kPack16Smem, s>>>(p); }
-    else { FPNGB_SET_SMEM(pack_rows16_kernel<3>, kPack16Smem); pack_rows16_kernel<3><<<grid, 32 * kPack16Rows, kPack16Smem, s>>>(p); }
+    if (chans == 4) { FPNGB_SET_SMEM(pack_rows16_kernel<4>, pack16_smem<4>()); pack_rows16_kernel<4><<<grid, 32 * kPack16Rows, pack16_smem<4>(), s>>>(p); }
+    else { FPNGB_SET_SMEM(pack_rows16_kernel<3>, pack16_smem<3>()); pack_rows16_kernel<3><<<grid, 32 * kPack16Rows, pack16_smem<3>(), s>>>(p); }
 }
 
 }  // namespace fpngb

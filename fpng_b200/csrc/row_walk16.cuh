@@ -3,10 +3,10 @@
 // Same tokenisation as row_walk.cuh (reference: fpng.cpp:1182-1243 / 1468-1558) with the
 // per-step warp-wide work (neighbour shuffle, ballot, run phase) amortised over 4x more pixels and with fully coalesced
 // 128-bit global loads:
-//   1. lane l issues cp.async (LDGSTS) copies of the 16-byte chunks #(j*32 + l), j = 0..CHANS-1, of the step's cur and
-//      prev scanline bytes (coalesced in HBM) into a padded shared-memory tile, one step ahead of the computation;
-//   2. each lane reads its own 16 consecutive pixels (80-byte slots: conflict-free 128-bit reads), subtracts the previous
-//      scanline (PNG filter 2 "Up", fpng.cpp:1605-1652) and accumulates the Adler-32 partial sums;
+//   1. one elected lane issues a TMA bulk copy (cp.async.bulk + mbarrier) of the step's 512 cur and prev pixels into the
+//      warp's shared-memory tile, one step ahead of the computation;
+//   2. each lane reads its own 16 consecutive pixels with 128-bit shared loads, subtracts the previous scanline (PNG
+//      filter 2 "Up", fpng.cpp:1605-1652) and accumulates the Adler-32 partial sums;
 //   3. equality with the left pixel gives a 16-bit mask per lane; the run phase entering the lane is one ballot + one
 //      shuffle; the lane then walks its pixels.
 // Requires every scanline to start 16-byte aligned and bpl % 16 == 0 (RGBA: w % 4 == 0, RGB: w % 16 == 0); other
@@ -18,82 +18,105 @@ namespace fpngb {
 
 constexpr int kPix16 = 16;                       // pixels per lane per step
 constexpr int kStep16 = 32 * kPix16;             // pixels per warp step
-constexpr int kTileLaneBytes = 80;               // padded per-lane slot in the transpose tile
-constexpr int kTileBytes = 32 * kTileLaneBytes;  // per warp
+// ---- TMA (bulk async copy) staging ------------------------------------------------------------------------------
+// One elected lane per warp issues ONE `cp.async.bulk` per scanline per step (cur and prev: 512 pixels = 1536 / 2048
+// contiguous bytes each) into the warp's shared-memory tile and arms the warp's mbarrier with the byte count; all lanes
+// wait on the mbarrier phase, read their own 16 pixels (48 / 64 contiguous bytes per lane) into registers, and the next
+// step's copies are issued while this step is processed.  SASS: UBLKCP + SYNCS.
+constexpr int kTileBytes = 2048;                        // one scanline step: 512 pixels x (3|4) bytes <= 2048
+constexpr int kTileStageBytes = 2 * kTileBytes;         // cur + prev
+constexpr int kTileLaneBytes = 80;                      // padded per-lane slot of the cp.async (RGBA) variant
+constexpr int kTileWarpBytes = 2 * 32 * kTileLaneBytes + 16;   // max over both variants: 2 x 2560 (padded cur+prev) / 4096 + mbarrier
 
-constexpr int kTileStageBytes = 2 * kTileBytes;         // cur + prev tiles of one pipeline stage
-constexpr int kTileWarpBytes = kTileStageBytes;         // one stage: the next step is fetched as soon as this one is in registers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid)
+__device__ __forceinline__ void mbar_init(void* mbar, uint32_t count)
 {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    const int src_bytes = valid ? 16 : 0;                // 0 -> the 16 destination bytes are zero-filled, nothing is read
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void* mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* mbar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, void* mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
 
-// Scanline staging through shared memory with cp.async (LDGSTS): lane l copies the step's 16-byte chunks #(j*32 + l)
-// (coalesced in global memory) straight into the slot of the lane that owns those pixels (80-byte padded slots, so the
-// later 128-bit reads are bank-conflict free).  The tile is consumed into registers first, then refilled for step s+1
-// while step s is being processed.
 template <int CHANS>
-struct Walk16 {
+struct Walk16Tma {
     static constexpr int kWords = 4 * CHANS;     // filtered words per lane per step (16 pixels)
-    uint32_t soff[CHANS];                        // byte offsets inside a tile where this lane's copies land
+    static constexpr uint32_t kStepBytes = kStep16 * CHANS;
+    static constexpr uint32_t kMbarOfs = kTileStageBytes;     // the warp's mbarrier sits behind the two 2 KiB tiles
+    static constexpr int kWarpBytes = kTileStageBytes + 16;   // shared memory per warp
 
-    __device__ __forceinline__ void init(uint32_t lane)
+    __device__ __forceinline__ void init(uint32_t lane, uint8_t* warp_tiles)
     {
-#pragma unroll
-        for (int j = 0; j < CHANS; j++) {
-            const uint32_t q = j * 32u + lane;   // chunk index inside the step
-            soff[j] = (q / CHANS) * kTileLaneBytes + (q % CHANS) * 16u;
-        }
+        if (lane == 0) mbar_init(warp_tiles + kMbarOfs, 1);
+        __syncwarp();
     }
 
-    // issue the copies of one step into pipeline stage `stage` (0/1) of this warp's tile memory
+    // issue the bulk copies of one step (lane 0 only) into this warp's tile
     __device__ __forceinline__ void prefetch(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev, uint32_t step, uint32_t bpl,
-                                             uint32_t lane, uint8_t* warp_tiles, uint32_t stage) const
+                                             uint32_t lane, uint8_t* warp_tiles) const
     {
-        uint8_t* tc = warp_tiles + stage * kTileStageBytes;
-        uint8_t* tp = tc + kTileBytes;
-        const uint32_t step_base = step * (uint32_t)(kStep16 * CHANS);
-#pragma unroll
-        for (int j = 0; j < CHANS; j++) {
-            const uint32_t b = step_base + (j * 32u + lane) * 16u;
-            const bool valid = b < bpl;
-            cp_async16(tc + soff[j], cur + (valid ? b : 0u), valid);
-            if (prev) cp_async16(tp + soff[j], prev + (valid ? b : 0u), valid);
+        if (lane == 0) {
+            const uint32_t b = step * kStepBytes;
+            const uint32_t bytes = min(kStepBytes, bpl - b);              // bpl % 16 == 0
+            void* mbar = warp_tiles + kMbarOfs;
+            // order the previous step's generic-proxy reads of the tile before the async-proxy writes
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            mbar_expect_tx(mbar, prev ? 2u * bytes : bytes);
+            tma_bulk_g2s(warp_tiles, cur + b, bytes, mbar);
+            if (prev) tma_bulk_g2s(warp_tiles + kTileBytes, prev + b, bytes, mbar);
         }
-        cp_async_commit();
     }
 
-    // read the lane's 16 pixels of a landed stage, apply the Up filter (fpng.cpp:1605-1652), optionally add the Adler
-    // partials (sum of bytes, position-weighted sum) of these 16*CHANS bytes
+    // wait for the step to land, read the lane's 16 pixels, apply the Up filter (fpng.cpp:1605-1652), optionally add the
+    // Adler partials (sum of bytes, position-weighted sum) of these 16*CHANS bytes
     template <bool kAdler>
-    __device__ __forceinline__ void consume(bool have_prev, uint32_t step, uint32_t lane, const uint8_t* warp_tiles, uint32_t stage,
+    __device__ __forceinline__ void consume(bool have_prev, uint32_t step, uint32_t bpl, uint32_t lane, uint8_t* warp_tiles,
                                             uint32_t (&dw)[kWords], uint32_t& sumA, unsigned long long& sumB) const
     {
-        const uint8_t* tc = warp_tiles + stage * kTileStageBytes + lane * kTileLaneBytes;
+        mbar_wait(warp_tiles + kMbarOfs, step & 1u);
+        const uint8_t* tc = warp_tiles + lane * (16 * CHANS);
         const uint8_t* tp = tc + kTileBytes;
-        const uint32_t lane_base = (step * (uint32_t)kStep16 + lane * (uint32_t)kPix16) * CHANS;     // byte offset of the lane's first byte in the row
+        const uint32_t lane_base = step * kStepBytes + lane * (16u * CHANS);     // byte offset of the lane's first byte in the row
 #pragma unroll
         for (int i = 0; i < CHANS; i++) {
-            uint4 d = *reinterpret_cast<const uint4*>(tc + i * 16);
-            if (have_prev) {
-                const uint4 q = *reinterpret_cast<const uint4*>(tp + i * 16);
-                d.x = vsub4(d.x, q.x); d.y = vsub4(d.y, q.y); d.z = vsub4(d.z, q.z); d.w = vsub4(d.w, q.w);
-            }
-            if (kAdler) {
-                uint32_t t1 = __dp4a(d.x, 0x01010101u, 0u), t2 = __dp4a(d.x, 0x03020100u, 0u);
-                t1 = __dp4a(d.y, 0x01010101u, t1); t2 = __dp4a(d.y, 0x07060504u, t2);
-                t1 = __dp4a(d.z, 0x01010101u, t1); t2 = __dp4a(d.z, 0x0B0A0908u, t2);
-                t1 = __dp4a(d.w, 0x01010101u, t1); t2 = __dp4a(d.w, 0x0F0E0D0Cu, t2);
-                sumA += t1;
-                sumB += (unsigned long long)(lane_base + 16u * i) * t1 + t2;
+            uint4 d = make_uint4(0, 0, 0, 0);
+            if (lane_base + 16u * i < bpl) {                                     // bytes beyond the scanline were not copied
+                d = *reinterpret_cast<const uint4*>(tc + i * 16);
+                if (have_prev) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(tp + i * 16);
+                    d.x = vsub4(d.x, q.x); d.y = vsub4(d.y, q.y); d.z = vsub4(d.z, q.z); d.w = vsub4(d.w, q.w);
+                }
+                if (kAdler) {
+                    uint32_t t1 = __dp4a(d.x, 0x01010101u, 0u), t2 = __dp4a(d.x, 0x03020100u, 0u);
+                    t1 = __dp4a(d.y, 0x01010101u, t1); t2 = __dp4a(d.y, 0x07060504u, t2);
+                    t1 = __dp4a(d.z, 0x01010101u, t1); t2 = __dp4a(d.z, 0x0B0A0908u, t2);
+                    t1 = __dp4a(d.w, 0x01010101u, t1); t2 = __dp4a(d.w, 0x0F0E0D0Cu, t2);
+                    sumA += t1;
+                    sumB += (unsigned long long)(lane_base + 16u * i) * t1 + t2;
+                }
             }
             dw[4 * i] = d.x; dw[4 * i + 1] = d.y; dw[4 * i + 2] = d.z; dw[4 * i + 3] = d.w;
         }
+        __syncwarp();                                                            // every lane has its pixels: the tile may be refilled
     }
 
     __device__ __forceinline__ static void pixels(const uint32_t (&dw)[kWords], uint32_t (&px)[16])
@@ -113,6 +136,85 @@ struct Walk16 {
         }
     }
 };
+
+// ---- cp.async (LDGSTS) staging into padded slots ------------------------------------------------------------------
+// RGBA variant: 64 contiguous bytes per lane would make the 128-bit shared reads 4-way bank conflicted, and that costs
+// more than it saves on the LSU-heavy RGBA kernels (measured: scan 1.71 ms with the linear TMA tile vs 1.48 ms padded).
+// Lane l copies the 16-byte chunks #(j*32 + l) (coalesced in HBM) into the 80-byte padded slot of the lane that owns the
+// pixels; same single-stage pipeline (consume into registers, then refill for the next step).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid)
+{
+    const int src_bytes = valid ? 16 : 0;                // 0 -> the 16 destination bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+
+template <int CHANS>
+struct Walk16Padded {
+    static constexpr int kWords = 4 * CHANS;
+    static constexpr int kPadTile = 32 * kTileLaneBytes;
+    static constexpr int kWarpBytes = 2 * kPadTile;           // shared memory per warp
+    uint32_t soff[CHANS];                        // byte offsets inside a tile where this lane's copies land
+
+    __device__ __forceinline__ void init(uint32_t lane, uint8_t*)
+    {
+#pragma unroll
+        for (int j = 0; j < CHANS; j++) {
+            const uint32_t q = j * 32u + lane;   // chunk index inside the step
+            soff[j] = (q / CHANS) * kTileLaneBytes + (q % CHANS) * 16u;
+        }
+    }
+    __device__ __forceinline__ void prefetch(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev, uint32_t step, uint32_t bpl,
+                                             uint32_t lane, uint8_t* warp_tiles) const
+    {
+        const uint32_t step_base = step * (uint32_t)(kStep16 * CHANS);
+#pragma unroll
+        for (int j = 0; j < CHANS; j++) {
+            const uint32_t b = step_base + (j * 32u + lane) * 16u;
+            const bool valid = b < bpl;
+            cp_async16(warp_tiles + soff[j], cur + (valid ? b : 0u), valid);
+            if (prev) cp_async16(warp_tiles + kPadTile + soff[j], prev + (valid ? b : 0u), valid);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    template <bool kAdler>
+    __device__ __forceinline__ void consume(bool have_prev, uint32_t step, uint32_t, uint32_t lane, uint8_t* warp_tiles,
+                                            uint32_t (&dw)[kWords], uint32_t& sumA, unsigned long long& sumB) const
+    {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+        const uint8_t* tc = warp_tiles + lane * kTileLaneBytes;
+        const uint8_t* tp = tc + kPadTile;
+        const uint32_t lane_base = (step * (uint32_t)kStep16 + lane * (uint32_t)kPix16) * CHANS;
+#pragma unroll
+        for (int i = 0; i < CHANS; i++) {
+            uint4 d = *reinterpret_cast<const uint4*>(tc + i * 16);
+            if (have_prev) {
+                const uint4 q = *reinterpret_cast<const uint4*>(tp + i * 16);
+                d.x = vsub4(d.x, q.x); d.y = vsub4(d.y, q.y); d.z = vsub4(d.z, q.z); d.w = vsub4(d.w, q.w);
+            }
+            if (kAdler) {
+                uint32_t t1 = __dp4a(d.x, 0x01010101u, 0u), t2 = __dp4a(d.x, 0x03020100u, 0u);
+                t1 = __dp4a(d.y, 0x01010101u, t1); t2 = __dp4a(d.y, 0x07060504u, t2);
+                t1 = __dp4a(d.z, 0x01010101u, t1); t2 = __dp4a(d.z, 0x0B0A0908u, t2);
+                t1 = __dp4a(d.w, 0x01010101u, t1); t2 = __dp4a(d.w, 0x0F0E0D0Cu, t2);
+                sumA += t1;
+                sumB += (unsigned long long)(lane_base + 16u * i) * t1 + t2;
+            }
+            dw[4 * i] = d.x; dw[4 * i + 1] = d.y; dw[4 * i + 2] = d.z; dw[4 * i + 3] = d.w;
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ static void pixels(const uint32_t (&dw)[kWords], uint32_t (&px)[16])
+    {
+#pragma unroll
+        for (int k = 0; k < 16; k++) px[k] = dw[k];
+    }
+};
+
+// RGB: linear TMA tile (48-byte lane stride is bank-conflict free for 128-bit reads); RGBA: padded cp.async tile.
+template <int CHANS> struct Walk16Select { using type = Walk16Tma<CHANS>; };
+template <> struct Walk16Select<4> { using type = Walk16Padded<4>; };
+template <int CHANS> using Walk16 = typename Walk16Select<CHANS>::type;
 
 struct Lane16 {
     uint32_t eqm;      // bit k: pixel k equals its left neighbour (valid pixels only)
