@@ -8,7 +8,8 @@ namespace fpngb {
 
 constexpr int kScan16Rows = 8;                   // warps (scanlines) per CTA, scan
 constexpr int kPack16Rows = 4;                   // warps per CTA, pack (larger staging buffers)
-constexpr int kStage16Words = 1072;              // >= (31 + 12 + 512 * 66) / 32 + 1
+// staging words per warp step: lead-in (31) + filter literal (12) + 512 pixel slots of [pending match 18 bits][literal 12*CHANS bits]
+template <int CHANS> __host__ __device__ constexpr int stage16_words() { return ((31 + 12 + 512 * (18 + 12 * CHANS)) / 32 + 1 + 15) / 16 * 16; }
 
 __device__ __forceinline__ uint32_t byte1(uint32_t v) { return __byte_perm(v, 0u, 0x4441); }   // (v >> 8) & 0xFF in one PRMT
 __device__ __forceinline__ uint32_t byte2(uint32_t v) { return __byte_perm(v, 0u, 0x4442); }
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     uint32_t* s_lit = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * Walk16<CHANS>::kWarpBytes);
     uint32_t* s_match = s_lit + 256;
     uint32_t* s_stage_all = s_match + 88;
-    uint32_t* s_side_all = s_stage_all + kPack16Rows * kStage16Words;
+    uint32_t* s_side_all = s_stage_all + kPack16Rows * stage16_words<CHANS>();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t img = blockIdx.y;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     }
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = book->lit[i];
     if (threadIdx.x < 88) s_match[threadIdx.x] = book->match[threadIdx.x];
-    for (uint32_t i = lane; i < kStage16Words; i += 32) s_stage_all[warp * kStage16Words + i] = 0u;
+    for (uint32_t i = lane; i < (uint32_t)stage16_words<CHANS>(); i += 32) s_stage_all[warp * stage16_words<CHANS>() + i] = 0u;
     __syncthreads();
     if (y >= p.h) return;
 
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
     const uint8_t* prev = y ? cur - bpl : nullptr;
     uint32_t* file_words = reinterpret_cast<uint32_t*>(p.out + (size_t)img * p.out_stride);
-    uint32_t* stage = s_stage_all + warp * kStage16Words;
+    uint32_t* stage = s_stage_all + warp * stage16_words<CHANS>();
     uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
     const uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
     const uint32_t row_total = p.row_bits[(size_t)img * p.h + y];
@@ -402,7 +403,7 @@ bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t
 }
 
 template <int CHANS> constexpr size_t scan16_smem() { return kScan16Rows * Walk16<CHANS>::kWarpBytes + 256 + 96; }
-template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk16<CHANS>::kWarpBytes + (256 + 88 + kPack16Rows * kStage16Words + kPack16Rows * 32) * 4; }
+template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk16<CHANS>::kWarpBytes + (256 + 88 + kPack16Rows * stage16_words<CHANS>() + kPack16Rows * 32) * 4; }
 
 // opt in to > 48 KiB of dynamic shared memory (per kernel instantiation, once per process)
 #define FPNGB_SET_SMEM(kernel, bytes) do { static bool done_ = false; \
