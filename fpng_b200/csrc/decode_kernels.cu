@@ -264,27 +264,33 @@ struct DeltaSink {
     uint8_t* delta; uint32_t pitch, bpl, h;
     uint32_t row, col;            // position in the filtered stream; col 0 is the filter byte
     uint8_t* ptr;                 // address of the next data byte of the current row
-    uint32_t acc, nacc;           // nacc pending bytes for the aligned word ending just before ptr
+    uint32_t acc;                 // bytes [word(ptr), ptr) of the aligned word being filled, already in place
+    uint32_t first_off;           // offset inside that word of the first byte this thread owns (0 unless it started mid-word)
     __device__ __forceinline__ void init(uint8_t* d, uint32_t pitch_, uint32_t bpl_, uint32_t h_, unsigned long long out_pos)
     {
         delta = d; pitch = pitch_; bpl = bpl_; h = h_;
         row = (uint32_t)(out_pos / (bpl + 1ull)); col = (uint32_t)(out_pos % (bpl + 1ull));
         ptr = delta + (size_t)row * pitch + (col ? col - 1u : 0u);
-        acc = 0; nacc = 0;
+        acc = 0; first_off = (uint32_t)((uintptr_t)ptr & 3u);
     }
+    // store the bytes gathered so far for the (incomplete or partly owned) current word, one by one
     __device__ __forceinline__ void flush()
     {
-        for (uint32_t i = 0; i < nacc; i++) ptr[(int)i - (int)nacc] = (uint8_t)(acc >> (8u * i));
-        nacc = 0; acc = 0;
+        const uint32_t n = (uint32_t)((uintptr_t)ptr & 3u);
+        uint8_t* w = ptr - n;
+        for (uint32_t i = first_off; i < n; i++) w[i] = (uint8_t)(acc >> (8u * i));
+        acc = 0; first_off = n;
     }
-    __device__ __forceinline__ void next_row() { flush(); col = 0; row++; ptr = delta + (size_t)row * pitch; }
+    __device__ __forceinline__ void next_row() { flush(); col = 0; row++; ptr = delta + (size_t)row * pitch; first_off = 0; }
     // one data byte (col >= 1, row < h)
     __device__ __forceinline__ void put(uint32_t v)
     {
-        if (nacc == 0 && ((uintptr_t)ptr & 3u)) { *ptr++ = (uint8_t)v; }
-        else {
-            acc |= v << (8u * nacc); nacc++; ptr++;
-            if (nacc == 4u) { *reinterpret_cast<uint32_t*>(ptr - 4) = acc; acc = 0; nacc = 0; }
+        acc |= v << (8u * ((uint32_t)(uintptr_t)ptr & 3u));
+        ptr++;
+        if (((uintptr_t)ptr & 3u) == 0) {                  // word complete
+            if (first_off == 0) *reinterpret_cast<uint32_t*>(ptr - 4) = acc;
+            else { for (uint32_t i = first_off; i < 4u; i++) ptr[(int)i - 4] = (uint8_t)(acc >> (8u * i)); first_off = 0; }
+            acc = 0;
         }
         if (++col > bpl) next_row();
     }
@@ -332,13 +338,14 @@ __device__ __forceinline__ SubScan decode_range(const Stream& st, const uint32_t
                 lits = (lits >> 8) | (s << 24);
                 if (two) lits = (lits >> 8) | (lut_sym1(e) << 24);
             } else {
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    if (k == 1 && !two) break;
-                    const uint32_t v = k ? lut_sym1(e) : s;
+                // first literal, then (predicated) the fused second one; a literal at column 0 is the row's filter byte
+                lits = (lits >> 8) | (s << 24);
+                if (sink.col == 0) { if (sink.row >= h || s != (sink.row ? 2u : 0u)) { *err = 1; break; } sink.col = 1; }   // fpng.cpp:2264, 2642
+                else sink.put(s);
+                if (two) {
+                    const uint32_t v = lut_sym1(e);
                     lits = (lits >> 8) | (v << 24);
-                    if (sink.row >= h) *err = 1;
-                    else if (sink.col == 0) { if (v != (sink.row ? 2u : 0u)) *err = 1; sink.col = 1; }   // fpng.cpp:2264, 2642
+                    if (sink.col == 0) { if (sink.row >= h || v != (sink.row ? 2u : 0u)) { *err = 1; break; } sink.col = 1; }
                     else sink.put(v);
                 }
             }
