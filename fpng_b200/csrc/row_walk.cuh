@@ -185,23 +185,44 @@ __device__ __forceinline__ uint32_t warp_excl_scan_u32(uint32_t v, uint32_t lane
     return s - v;
 }
 
-// Stored-block fallback for one row: stream byte s (row y, column t; t == 0 is the filter byte 0) lands at
-// zlib offset 2 + 5 * (s / 65535 + 1) + s.  Also produces the row's Adler partials over the raw bytes.
+// Stored-block fallback for one row (fpng.cpp:818-866): stream byte s (row y, column t; t == 0 is the filter byte 0)
+// lands at zlib offset 2 + 5 * (s / 65535 + 1) + s.  The row is copied block segment by block segment with 32-bit stores
+// (source words rebuilt from byte loads that hit L1); also produces the row's Adler partials over the raw bytes.
 __device__ __forceinline__ void store_row_raw(const uint8_t* __restrict__ cur, uint8_t* __restrict__ zl, uint32_t y, uint32_t bpl,
                                               uint32_t lane, uint2* adler_out)
 {
     const unsigned long long n = (unsigned long long)bpl + 1ull;
     const unsigned long long s0 = (unsigned long long)y * n;
-    unsigned long long A = 0, B = 0;
-    for (unsigned long long t = lane; t < n; t += 32) {
-        const uint32_t v = t ? ld_u8(cur + (t - 1)) : 0u;
-        const unsigned long long s = s0 + t;
-        zl[2ull + 5ull * (s / 65535ull + 1ull) + s] = (uint8_t)v;
-        A += v; B += t * v;
+    unsigned long long A = 0, B = 0;                      // sum v, sum t*v  (t = index inside the row's stream)
+    unsigned long long t = 0;                              // next stream index of the row to copy
+    while (t < n) {
+        const unsigned long long s = s0 + t, blk = s / 65535ull;
+        const unsigned long long seg = min(n - t, (blk + 1ull) * 65535ull - s);      // bytes until the row or the block ends
+        uint8_t* dst = zl + 2ull + 5ull * (blk + 1ull) + s;
+        // source of stream index t is 0 (filter) for t == 0, cur[t-1] otherwise
+        unsigned long long done = 0;
+        if (t == 0) { if (lane == 0) dst[0] = 0; done = 1; }
+        const uint8_t* src = cur + (t + done - 1ull);
+        uint8_t* d = dst + done;
+        const unsigned long long len = seg - done;
+        const uint32_t head = (uint32_t)min((unsigned long long)((4u - ((uintptr_t)d & 3u)) & 3u), len);
+        if (lane < head) { const uint32_t v = ld_u8(src + lane); d[lane] = (uint8_t)v; A += v; B += (t + done + lane) * v; }
+        const unsigned long long body = (len - head) >> 2;
+        const uint8_t* sb = src + head; uint8_t* db = d + head;
+        const unsigned long long tb = t + done + head;
+        for (unsigned long long j = lane; j < body; j += 32) {
+            const uint8_t* q = sb + 4ull * j;
+            const uint32_t v = ld_u8(q) | (ld_u8(q + 1) << 8) | (ld_u8(q + 2) << 16) | (ld_u8(q + 3) << 24);
+            *reinterpret_cast<uint32_t*>(db + 4ull * j) = v;
+            const uint32_t t1 = __dp4a(v, 0x01010101u, 0u), t2 = __dp4a(v, 0x03020100u, 0u);
+            A += t1; B += (tb + 4ull * j) * t1 + t2;
+        }
+        const uint32_t tail = (uint32_t)((len - head) & 3ull);
+        if (lane < tail) { const unsigned long long o = head + 4ull * body + lane; const uint32_t v = ld_u8(src + o); d[o] = (uint8_t)v; A += v; B += (t + done + o) * v; }
+        t += seg;
     }
     A = warp_sum_u64(A); B = warp_sum_u64(B);
     if (lane == 0) *adler_out = make_uint2((uint32_t)(A % kAdlerMod), (uint32_t)((n * A - B) % kAdlerMod));
 }
-
 
 }  // namespace fpngb

@@ -215,3 +215,24 @@ def test_concurrent_host_threads_and_streams(gpu, oracle):
             sz = s.cpu().numpy().astype(np.int64)
             for i in range(6):
                 assert bytes(o[i, : sz[i]].cpu().numpy()) == oracle.encode(t[i].cpu().numpy(), 512, 64, 4, 0)
+
+
+def test_random_dimension_fuzz_like_reference_E(gpu, oracle):
+    """The reference's `-E` fuzz (src/fpng_test.cpp:617-682): random width/height up to 8193, random 3/4 channels, uniform
+    random pixels (stored-block path), verified by decoding; here additionally byte-compared with the oracle."""
+    rs = np.random.RandomState(2024)
+    dims = [(int(rs.randint(1, 2100)), int(rs.randint(1, 260))) for _ in range(10)] + [(8193, 3), (5, 8193), (8192, 2), (65540, 1), (21846, 4)]
+    for i, (w, h) in enumerate(dims):
+        c = 4 if rs.randint(0, 2) else 3
+        img = rs.randint(0, 256, size=(h, w, c), dtype=np.uint8)
+        ok, png = gpu.fpng_encode_image_to_memory(img, w, h, c, 0)
+        assert ok and png == oracle.encode(img, w, h, c, 0), (w, h, c)
+        st, px, ww, hh, cc = gpu.fpng_decode_memory(png, c)
+        assert st == 0 and (ww, hh, cc) == (w, h, c) and np.array_equal(px, img.reshape(-1)), (w, h, c)
+        if i % 3 == 0:   # compressible content at the same odd shapes
+            img2 = imagegen.make("mut", w, h, c, i)
+            for flags in (0, 1):
+                ok, png = gpu.fpng_encode_image_to_memory(img2, w, h, c, flags)
+                assert ok and png == oracle.encode(img2, w, h, c, flags), (w, h, c, flags)
+                st, px, *_ = gpu.fpng_decode_memory(png, 7 - c)
+                assert st == 0
