@@ -394,7 +394,33 @@ def run_ours(args, wl):
                           "pixels_match_input": dec_ok, "algorithmic_gbs": dec_bytes / 1e9 / (dms / 1e3),
                           "frac_of_peak": dec_bytes / 1e9 / (dms / 1e3) / peak,
                           "input": "this rank's GPU-encoded files (byte-identical to reference-written files), device resident"}
-        del files_dev, px
+        # end to end through the C ABI with host buffers: files (pinned) -> H2D -> kernels -> D2H pixels (pinned)
+        hfiles = torch.zeros((n, fstride), dtype=torch.uint8).pin_memory()
+        hfiles.copy_(files_dev.cpu())
+        hpx = torch.empty((n, h * w * c), dtype=torch.uint8).pin_memory()
+        ptrs = [hfiles.data_ptr() + i * fstride for i in range(n)]
+
+        def de2e():
+            rc, ww2, hh2, cc2, stt = fpng_b200.decode_batch_host(ptrs, fsizes, c, hpx, h * w * c)
+            if rc or (stt != 0).any():
+                raise RuntimeError("fpngb_decode_batch_host failed")
+
+        de2e()
+        if world > 1:
+            dist.barrier()
+        ksteps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            de2e()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        line["decode"]["e2e"] = {"value": world * n * w * h * ksteps / MP / float(tt.item()), "unit": "MP/s",
+                                 "h2d_bytes_per_step": int(fsizes.astype(np.int64).sum()), "d2h_bytes_per_step": n * w * h * c + 4 * n,
+                                 "api": "fpngb_decode_batch_host (C ABI, pinned host buffers, blocking)",
+                                 "pixels_match_input": bool(torch.equal(hpx.view(n, h, w, c), batch.cpu()))}
+        del files_dev, px, hfiles, hpx
 
     # ---- the one NCCL gather of the encoded buffers (north_star), timed separately from the per-rank encode
     if world > 1:

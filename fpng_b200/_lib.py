@@ -47,6 +47,8 @@ def lib() -> C.CDLL:
                                             C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.fpngb_compact_batch_device.restype = C.c_int
     L.fpngb_compact_batch_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.fpngb_decode_batch_host.restype = C.c_int
+    L.fpngb_decode_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, u32p, u32p, u32p, C.c_void_p]
     L.fpngb_crc32.restype = C.c_uint32
     L.fpngb_crc32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
     L.fpngb_adler32.restype = C.c_uint32

@@ -202,3 +202,18 @@ def decode_batch_device(files_dev, sizes, idat_ofs, idat_len, w: int, h: int, ch
                                          status.data_ptr(), s)
     check(rc, "decode_batch_device")
     return out, status
+
+
+def decode_batch_host(file_ptrs, sizes, desired_channels: int, out, out_stride: int):
+    """Pipelined host-buffer batch decode (fpngb_decode_batch_host).  file_ptrs: array of host addresses (uint64), sizes:
+    uint32 array, out: host buffer (numpy uint8 / pinned torch tensor) with out_stride bytes per image.
+    Returns (rc, w, h, chans, status[n])."""
+    n = len(sizes)
+    ptrs = (C.c_void_p * n)(*[int(p) for p in file_ptrs])
+    sz = np.ascontiguousarray(sizes, dtype=np.uint32)
+    status = np.zeros(n, dtype=np.int32)
+    w, h, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    optr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+    rc = lib().fpngb_decode_batch_host(ptrs, sz.ctypes.data_as(C.c_void_p), n, desired_channels, optr, out_stride,
+                                       C.byref(w), C.byref(h), C.byref(c), status.ctypes.data_as(C.c_void_p))
+    return rc, w.value, h.value, c.value, status

@@ -168,6 +168,92 @@ int fpngb_get_info(const void* file, uint32_t size, uint32_t* w, uint32_t* h, ui
     return st;
 }
 
+// Pipelined host-buffer batch decode: per chunk the files go H2D, the decode kernels run, the pixels come back D2H;
+// three slots keep copies and kernels of neighbouring chunks overlapped.  Files that fail the container walk keep their
+// status and are skipped; all decodable files must share width/height/channels.
+int fpngb_decode_batch_host(const void* const* files, const uint32_t* sizes, uint32_t n, uint32_t desired, void* out, size_t out_stride,
+                            uint32_t* w_out, uint32_t* h_out, uint32_t* chans_out, int* status)
+{
+    Context& c = context();
+    if (!c.ready) return FPNGB_ERR_NOT_INITIALIZED;
+    if (!files || !sizes || !out || !status || n == 0 || (desired != 3 && desired != 4)) return FPNGB_ERR_INVALID_ARG;
+    std::vector<FileDesc> fds(n);
+    uint32_t W = 0, H = 0, C = 0, max_size = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t ww = 0, hh = 0, cc = 0, io = 0, il = 0;
+        status[i] = (!files[i] || !sizes[i]) ? FPNGB_DECODE_INVALID_ARG : container_info((const uint8_t*)files[i], sizes[i], &ww, &hh, &cc, &io, &il);
+        fds[i] = FileDesc{sizes[i], io, il, 0};
+        if (status[i]) continue;
+        if (!W) { W = ww; H = hh; C = cc; }
+        else if (ww != W || hh != H || cc != C) return FPNGB_ERR_INVALID_ARG;
+        if (sizes[i] > max_size) max_size = sizes[i];
+    }
+    if (w_out) *w_out = W; if (h_out) *h_out = H; if (chans_out) *chans_out = C;
+    if (!W) return FPNGB_OK;                                   // nothing decodable: statuses say why
+    const uint64_t need = (uint64_t)W * H * desired;
+    if (need > 0xFFFFFFFFull) { for (uint32_t i = 0; i < n; i++) if (!status[i]) status[i] = FPNGB_DECODE_FAILED_DIMENSIONS_TOO_LARGE; return FPNGB_OK; }
+    if (out_stride < need) return FPNGB_ERR_BUFFER_TOO_SMALL;
+    std::lock_guard<std::mutex> lk(c.mu);
+    FPNGB_CUDA_OK(cudaSetDevice(c.device));
+
+    constexpr int kSlots = 3;
+    const size_t fstride = align_up((size_t)max_size + 16, 16), pstride = align_up((size_t)need, 16);
+    uint32_t per_chunk = (uint32_t)(((size_t)64 << 20) / need); if (per_chunk < 1) per_chunk = 1; if (per_chunk > n) per_chunk = n;
+    const size_t slot_in = per_chunk * fstride, slot_out = per_chunk * pstride + align_up(per_chunk * 4, 256);
+    int rc = c.dev_in.reserve(kSlots * slot_in); if (rc) return rc;
+    rc = c.dev_out.reserve(kSlots * slot_out); if (rc) return rc;
+    rc = c.pin_small.reserve(kSlots * align_up(per_chunk * 4, 256)); if (rc) return rc;
+    if (!c.copy_in) { FPNGB_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking)); FPNGB_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking)); }
+    cudaEvent_t ev_in[kSlots], ev_done[kSlots], ev_out[kSlots];
+    for (int i = 0; i < kSlots; i++) { cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming); }
+    // decodable files, in order
+    std::vector<uint32_t> idx; idx.reserve(n);
+    for (uint32_t i = 0; i < n; i++) if (!status[i]) idx.push_back(i);
+    const uint32_t m = (uint32_t)idx.size(), nchunks = (m + per_chunk - 1) / per_chunk;
+    int result = FPNGB_OK;
+    std::vector<FileDesc> cf(per_chunk);
+    for (uint32_t k = 0; k < nchunks && result == FPNGB_OK; k++) {
+        const int sl = k % kSlots;
+        const uint32_t first = k * per_chunk, cnt = (first + per_chunk <= m) ? per_chunk : m - first;
+        if (k >= kSlots) {   // the slot's previous pixels and statuses have left the device
+            if (cudaEventSynchronize(ev_out[sl]) != cudaSuccess) { result = FPNGB_ERR_INTERNAL; break; }
+            const uint32_t pf = (k - kSlots) * per_chunk, pc = (pf + per_chunk <= m) ? per_chunk : m - pf;
+            const uint32_t* hs = (const uint32_t*)((uint8_t*)c.pin_small.p + sl * align_up(per_chunk * 4, 256));
+            for (uint32_t j = 0; j < pc; j++) status[idx[pf + j]] = hs[j] ? FPNGB_DECODE_NOT_FPNG : FPNGB_DECODE_SUCCESS;
+        }
+        uint8_t* din = (uint8_t*)c.dev_in.p + sl * slot_in;
+        uint8_t* dout = (uint8_t*)c.dev_out.p + sl * slot_out;
+        uint32_t* dst = (uint32_t*)(dout + per_chunk * pstride);
+        for (uint32_t j = 0; j < cnt; j++) {
+            const uint32_t i = idx[first + j];
+            cudaMemcpyAsync(din + j * fstride, files[i], sizes[i], cudaMemcpyHostToDevice, c.copy_in);
+            cf[j] = fds[i];
+        }
+        cudaEventRecord(ev_in[sl], c.copy_in);
+        cudaStreamWaitEvent(c.stream, ev_in[sl], 0);
+        rc = decode_batch_locked(din, fstride, cf.data(), cnt, W, H, C, desired, dout, pstride, dst, c.stream);
+        if (rc) { result = rc; break; }
+        cudaEventRecord(ev_done[sl], c.stream);
+        cudaStreamWaitEvent(c.copy_out, ev_done[sl], 0);
+        cudaMemcpyAsync((uint8_t*)c.pin_small.p + sl * align_up(per_chunk * 4, 256), dst, cnt * 4, cudaMemcpyDeviceToHost, c.copy_out);
+        for (uint32_t j = 0; j < cnt; j++)
+            cudaMemcpyAsync((uint8_t*)out + (size_t)idx[first + j] * out_stride, dout + j * pstride, need, cudaMemcpyDeviceToHost, c.copy_out);
+        cudaEventRecord(ev_out[sl], c.copy_out);
+    }
+    cudaStreamSynchronize(c.copy_in); cudaStreamSynchronize(c.stream); cudaStreamSynchronize(c.copy_out);
+    if (result == FPNGB_OK) {
+        for (uint32_t k = (nchunks > kSlots ? nchunks - kSlots : 0); k < nchunks; k++) {
+            const int sl = k % kSlots;
+            const uint32_t pf = k * per_chunk, pc = (pf + per_chunk <= m) ? per_chunk : m - pf;
+            const uint32_t* hs = (const uint32_t*)((uint8_t*)c.pin_small.p + sl * align_up(per_chunk * 4, 256));
+            for (uint32_t j = 0; j < pc; j++) status[idx[pf + j]] = hs[j] ? FPNGB_DECODE_NOT_FPNG : FPNGB_DECODE_SUCCESS;
+        }
+        if (cudaGetLastError() != cudaSuccess) result = FPNGB_ERR_INTERNAL;
+    }
+    for (int i = 0; i < kSlots; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_out[i]); }
+    return result;
+}
+
 int fpngb_get_info_ex(const void* file, uint32_t size, uint32_t* w, uint32_t* h, uint32_t* chans, uint32_t* idat_ofs, uint32_t* idat_len)
 {
     if (!file || !w || !h || !chans || !idat_ofs || !idat_len) return FPNGB_DECODE_INVALID_ARG;

@@ -98,6 +98,13 @@ FPNGB_API int fpngb_decode_batch_device(const void* d_files, size_t file_stride,
                                         uint32_t w, uint32_t h, uint32_t chans_in_file, uint32_t desired_chans,
                                         void* d_out, size_t out_stride, uint32_t* d_status, void* stream);
 
+/* Batch of n fpng files in HOST memory (files[i], sizes[i]; ideally pinned) -> pixels in host memory at out + i*out_stride.
+ * Container walk per file on the host (src/fpng.cpp:2930-3077), then H2D / decode kernels / D2H pipelined over chunks.
+ * status[i] receives the FPNGB_DECODE_* code of file i; all decodable files must share width/height/channels
+ * (returned in *w, *h, *chans).  Batch form of fpng_decode_memory (src/fpng.h:108). */
+FPNGB_API int fpngb_decode_batch_host(const void* const* files, const uint32_t* sizes, uint32_t n, uint32_t desired_chans,
+                                      void* out, size_t out_stride, uint32_t* w, uint32_t* h, uint32_t* chans, int* status);
+
 /* fpngb_get_info plus the location of the IDAT chunk (offset of the chunk's length field, and the IDAT length). */
 FPNGB_API int fpngb_get_info_ex(const void* file, uint32_t size, uint32_t* w, uint32_t* h, uint32_t* chans,
                                 uint32_t* idat_ofs, uint32_t* idat_len);

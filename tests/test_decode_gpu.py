@@ -109,3 +109,21 @@ def test_encode_decode_round_trip_full_size(gpu):
         torch.cuda.synchronize()
         assert (status.cpu().numpy() == 0).all()
         assert torch.equal(px, dev)
+
+
+def test_decode_batch_host(gpu, oracle):
+    """fpngb_decode_batch_host: pipelined host batch; bad files keep their container status and are skipped."""
+    w, h, c, n = 300, 40, 3, 11
+    imgs = [imagegen.make(["g1", "g0", "g2", "runs"][i % 4], w, h, c, i) for i in range(n)]
+    files = [np.frombuffer(oracle.encode(im, w, h, c, i % 3), dtype=np.uint8).copy() for i, im in enumerate(imgs)]
+    files[4] = files[4].copy(); files[4][0] = 0                      # not a PNG
+    files[7] = files[7].copy(); files[7][90] ^= 0x10                 # corrupt stream -> NOT_FPNG (or still valid: compare with oracle)
+    for d in (3, 4):
+        out = np.zeros((n, w * h * d), np.uint8)
+        rc, ww, hh, cc, status = gpu.decode_batch_host([f.ctypes.data for f in files], [f.size for f in files], d, out, w * h * d)
+        assert rc == 0 and (ww, hh, cc) == (w, h, c)
+        for i in range(n):
+            est, epx, *_ = oracle.decode(files[i].tobytes(), d)
+            assert status[i] == est, (i, status[i], est)
+            if est == 0:
+                assert np.array_equal(out[i], epx), i
