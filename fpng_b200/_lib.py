@@ -49,6 +49,13 @@ def lib() -> C.CDLL:
     L.fpngb_compact_batch_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.fpngb_decode_batch_host.restype = C.c_int
     L.fpngb_decode_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, u32p, u32p, u32p, C.c_void_p]
+    L.fpngb_train_accumulate_device.restype = C.c_int
+    L.fpngb_train_accumulate_device.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.fpngb_create_dynamic_block_prefix.restype = C.c_int
+    L.fpngb_create_dynamic_block_prefix.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64),
+                                                    C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+    L.fpngb_set_static_table.restype = C.c_int
+    L.fpngb_set_static_table.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]
     L.fpngb_crc32.restype = C.c_uint32
     L.fpngb_crc32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
     L.fpngb_adler32.restype = C.c_uint32

@@ -217,3 +217,34 @@ def decode_batch_host(file_ptrs, sizes, desired_channels: int, out, out_stride: 
     rc = lib().fpngb_decode_batch_host(ptrs, sz.ctypes.data_as(C.c_void_p), n, desired_channels, optr, out_stride,
                                        C.byref(w), C.byref(h), C.byref(c), status.ctypes.data_as(C.c_void_p))
     return rc, w.value, h.value, c.value, status
+
+
+# ---- static-table training (reference: FPNG_TRAIN_HUFFMAN_TABLES / fpng_test -t; src/fpng.h:114-120) ----
+def train_accumulate_device(images, counts=None, stream=None):
+    """Adds the 16-bit scaled symbol counts of every image of a CUDA uint8 batch [n, h, w, chans] to counts[288] (uint64)."""
+    import torch
+
+    assert images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous() and images.dim() == 4
+    n, h, w, c = images.shape
+    if counts is None:
+        counts = np.zeros(288, dtype=np.uint64)
+    s = stream if stream is not None else torch.cuda.current_stream(images.device).cuda_stream
+    check(lib().fpngb_train_accumulate_device(images.data_ptr(), h * w * c, n, w, h, c, counts.ctypes.data_as(C.c_void_p), s), "train_accumulate_device")
+    return counts
+
+
+def create_dynamic_block_prefix(counts, num_chans: int):
+    """src/fpng.cpp:910. Returns (prefix bytes, bit_buf, bit_buf_size, codes[288], code sizes[288])."""
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    prefix = np.zeros(4096, np.uint8); n = C.c_size_t(); bb = C.c_uint64(); bs = C.c_int()
+    codes = np.zeros(288, np.uint32); sizes = np.zeros(288, np.uint8)
+    check(lib().fpngb_create_dynamic_block_prefix(counts.ctypes.data_as(C.c_void_p), num_chans, prefix.ctypes.data_as(C.c_void_p), prefix.size,
+                                                  C.byref(n), C.byref(bb), C.byref(bs), codes.ctypes.data_as(C.c_void_p),
+                                                  sizes.ctypes.data_as(C.c_void_p)), "create_dynamic_block_prefix")
+    return prefix[: n.value].tobytes(), bb.value, bs.value, codes, sizes
+
+
+def set_static_table(num_chans: int, prefix: bytes = b"", bit_buf: int = 0, bit_buf_size: int = 0) -> None:
+    """Install a trained 1-pass table for num_chans (empty prefix restores the built-in table)."""
+    a = np.frombuffer(prefix, dtype=np.uint8) if prefix else np.zeros(1, np.uint8)
+    check(lib().fpngb_set_static_table(num_chans, a.ctypes.data_as(C.c_void_p), len(prefix), bit_buf, bit_buf_size), "set_static_table")

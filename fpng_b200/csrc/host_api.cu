@@ -254,7 +254,7 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
         FPNGB_CUDA_OK(cudaMemsetAsync(ws.hist, 0, (size_t)n * 288 * 4, s));
         if (v2) launch_hist16(sp, n, chans, s); else launch_scan(sp, n, chans, mode, true, s);
         prof_mark(ps, kProfHist, s);
-        HuffParams hp{ws.hist, ws.books, chans};
+        HuffParams hp{ws.hist, ws.books, chans, 0u};
         launch_huffman_build(hp, n, s);
         prof_mark(ps, kProfHuff, s);
         count_launch(2);
@@ -560,6 +560,111 @@ int fpngb_compact_batch_device(const void* d_files, size_t stride, const uint32_
     launch_compact((const uint8_t*)d_files, stride, d_sizes, n, (uint8_t*)d_dst, dst_cap, (unsigned long long*)d_offsets, (cudaStream_t)stream);
     count_launch(2);
     FPNGB_CUDA_OK(cudaGetLastError());
+    return FPNGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Static-table training (reference: fpng_test -t, src/fpng_test.cpp:766-963, and
+// create_dynamic_block_prefix, src/fpng.cpp:909-988).  The GPU part is the 288-bin histogram kernel of 2-pass mode.
+// ---------------------------------------------------------------------------------------------------------
+// Adds, for every image of a device-resident batch, its 16-bit scaled symbol counts to counts[288] -- exactly what the
+// reference accumulates in g_huff_counts while encoding with FPNG_ENCODE_SLOWER (fpng.cpp:751-755 after 1092-1094).
+int fpngb_train_accumulate_device(const void* d_pixels, size_t image_stride, uint32_t n, uint32_t w, uint32_t h, uint32_t chans,
+                                  uint64_t* counts, void* stream)
+{
+    if (!g_ctx.ready) return FPNGB_ERR_NOT_INITIALIZED;
+    if (!d_pixels || !counts || n == 0 || !valid_dims(w, h, chans) || image_stride < (size_t)w * h * chans || n > 65535) return FPNGB_ERR_INVALID_ARG;
+    Context& c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    FPNGB_CUDA_OK(cudaSetDevice(c.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace ws;
+    int rc = carve_workspace(c, n, h, w, true, ws); if (rc) return rc;
+    rc = c.ws_acquire(s); if (rc) return rc;
+    ScanParams sp{};
+    sp.pixels = (const uint8_t*)d_pixels; sp.image_stride = image_stride; sp.w = w; sp.h = h; sp.books = c.d_static_books; sp.book_stride = 0;
+    sp.row_bits = ws.row_bits; sp.row_adler = ws.row_adler; sp.st = ws.st; sp.hist = ws.hist; sp.lane_ofs = ws.lane_ofs; sp.lane_ofs_pitch = ws.lane_ofs_pitch;
+    FPNGB_CUDA_OK(cudaMemsetAsync(ws.hist, 0, (size_t)n * 288 * 4, s));
+    if (walk16_eligible(d_pixels, image_stride, w, chans)) launch_hist16(sp, n, chans, s);
+    else launch_scan(sp, n, chans, pick_load_mode(d_pixels, image_stride, w, chans), true, s);
+    count_launch(1);
+    std::vector<uint32_t> hh((size_t)n * 288);
+    FPNGB_CUDA_OK(cudaMemcpyAsync(hh.data(), ws.hist, hh.size() * 4, cudaMemcpyDeviceToHost, s));
+    rc = c.ws_release(s); if (rc) return rc;
+    FPNGB_CUDA_OK(cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t* f = &hh[(size_t)i * 288];
+        f[256] = 1;                                                   // fpng.cpp:1092
+        uint64_t total = 0;
+        for (int k = 0; k < 288; k++) total += f[k];
+        for (int k = 0; k < 288; k++) if (f[k]) { uint64_t v = (uint64_t)f[k] * 65535u / total; counts[k] += v < 1 ? 1 : v; }   // fpng.cpp:890
+    }
+    return FPNGB_OK;
+}
+
+// counts[288] -> pre-serialised block header ("prefix": zlib header, BFINAL, BTYPE=2, table description), the bits left
+// over after the last whole byte, and the code table.  Same signature/semantics as the reference's
+// create_dynamic_block_prefix (fpng.cpp:910).  The table construction runs in the Huffman-build kernel.
+int fpngb_create_dynamic_block_prefix(const uint64_t* counts, uint32_t chans, uint8_t* prefix, size_t prefix_cap, size_t* prefix_len,
+                                      uint64_t* bit_buf, int* bit_buf_size, uint32_t* codes288, uint8_t* sizes288)
+{
+    if (!g_ctx.ready) return FPNGB_ERR_NOT_INITIALIZED;
+    if (!counts || !prefix || !prefix_len || !bit_buf || !bit_buf_size || (chans != 3 && chans != 4)) return FPNGB_ERR_INVALID_ARG;
+    uint32_t freq[288];
+    for (int i = 0; i < 288; i++) freq[i] = (uint32_t)counts[i];       // fpng.cpp:933 (the reference stores the unshifted count)
+    for (int i = 0; i <= 256; i++) if (!freq[i]) freq[i] = 1;          // every literal / EOB codable (fpng.cpp:943-947)
+    for (uint32_t len = chans; len <= 258; len += chans) { uint32_t sym, xb, xv; deflate_len_code(len, sym, xb, xv); if (!freq[sym]) freq[sym] = 1; }
+    Context& c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    FPNGB_CUDA_OK(cudaSetDevice(c.device));
+    int rc = c.dev_in.reserve(288 * 4 + sizeof(CodeBook) + 512); if (rc) return rc;
+    uint32_t* d_hist = (uint32_t*)c.dev_in.p;
+    CodeBook* d_book = (CodeBook*)((uint8_t*)c.dev_in.p + 2048);
+    FPNGB_CUDA_OK(cudaMemcpyAsync(d_hist, freq, sizeof freq, cudaMemcpyHostToDevice, c.stream));
+    HuffParams hp{d_hist, d_book, chans, 1u};
+    launch_huffman_build(hp, 1, c.stream);
+    count_launch(1);
+    static CodeBook hb;
+    FPNGB_CUDA_OK(cudaMemcpyAsync(&hb, d_book, sizeof hb, cudaMemcpyDeviceToHost, c.stream));
+    FPNGB_CUDA_OK(cudaStreamSynchronize(c.stream));
+    const size_t nbytes = hb.hdr_bits / 8;
+    if (prefix_cap < nbytes) return FPNGB_ERR_BUFFER_TOO_SMALL;
+    memcpy(prefix, hb.hdr, nbytes);
+    *prefix_len = nbytes;
+    *bit_buf_size = (int)(hb.hdr_bits & 7);
+    *bit_buf = hb.hdr[nbytes] & ((1u << (hb.hdr_bits & 7)) - 1u);
+    // the exported code table covers every symbol with a code (canonical assignment, fpng.cpp:701-708), including
+    // length symbols this encoder never emits
+    uint16_t codes16[288];
+    canonical_codes(hb.sym_size, 288, codes16);
+    for (int i = 0; i < 288; i++) {
+        if (sizes288) sizes288[i] = hb.sym_size[i];
+        if (codes288) codes288[i] = codes16[i];
+    }
+    return FPNGB_OK;
+}
+
+// Install a trained 1-pass table (prefix bytes + leftover bits, as produced above or by the reference's trainer) for
+// `chans`; nbytes == 0 restores the built-in table.  Files written with it are ordinary fpng files.
+int fpngb_set_static_table(uint32_t chans, const uint8_t* prefix, size_t nbytes, uint32_t bit_buf, uint32_t bit_buf_size)
+{
+    if (!g_ctx.ready) return FPNGB_ERR_NOT_INITIALIZED;
+    if (chans != 3 && chans != 4) return FPNGB_ERR_INVALID_ARG;
+    Context& c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    FPNGB_CUDA_OK(cudaSetDevice(c.device));
+    static CodeBook cb;                                                // static: still alive while the async copy runs
+    bool ok;
+    if (nbytes == 0) ok = chans == 3 ? build_static_book(cb, kStaticHdrRGB, sizeof kStaticHdrRGB, kStaticHdrRGBTail, kStaticHdrRGBTailBits, 3)
+                                     : build_static_book(cb, kStaticHdrRGBA, sizeof kStaticHdrRGBA, kStaticHdrRGBATail, kStaticHdrRGBATailBits, 4);
+    else {
+        if (!prefix || nbytes + 1 > kMaxHdrBytes || bit_buf_size > 7) return FPNGB_ERR_INVALID_ARG;
+        ok = build_static_book(cb, prefix, (uint32_t)nbytes, bit_buf, bit_buf_size, chans);
+    }
+    if (!ok) return FPNGB_ERR_INVALID_ARG;
+    FPNGB_CUDA_OK(cudaDeviceSynchronize());                            // no encode may be using the old table
+    c.h_static_books[chans == 4 ? 1 : 0] = cb;
+    FPNGB_CUDA_OK(cudaMemcpy(c.d_static_books + (chans == 4 ? 1 : 0), &cb, sizeof cb, cudaMemcpyHostToDevice));
     return FPNGB_OK;
 }
 

@@ -118,11 +118,12 @@ __global__ void __launch_bounds__(32) huffman_build_kernel(HuffParams p)
 
     // --- 16-bit scaled counts (fpng.cpp:1092-1094 then 868-893, then 757)
     uint32_t part = 0;
-    for (uint32_t i = lane; i < 288; i += 32) part += (i == 256) ? 1u : hist[i];
+    const bool training = p.training != 0;
+    for (uint32_t i = lane; i < 288; i += 32) part += (i == 256 && !training) ? 1u : hist[i];
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
     const uint32_t total = part;
     for (uint32_t i = lane; i < 288; i += 32) {
-        const uint32_t f = (i == 256) ? 1u : hist[i];
+        const uint32_t f = (i == 256 && !training) ? 1u : hist[i];
         uint32_t v = 0;
         if (f) { v = (uint32_t)(((unsigned long long)f * 65535ull) / total); if (v < 1) v = 1; }
         if (i == 256) v = 1;

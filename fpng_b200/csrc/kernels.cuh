@@ -61,6 +61,7 @@ struct HuffParams {
     const uint32_t* hist;                         // [n*288]
     CodeBook* books;                              // [n]
     uint32_t chans;
+    uint32_t training;                            // 1: table training (fpng.cpp:909-988): symbol 256 keeps its own count in the scaling
 };
 
 void launch_scan(const ScanParams& p, uint32_t n, uint32_t chans, int mode, bool hist, cudaStream_t s);

@@ -119,6 +119,18 @@ FPNGB_API uint32_t fpngb_adler32(const void* data, size_t size, uint32_t adler);
 FPNGB_API int fpngb_compact_batch_device(const void* d_files, size_t stride, const uint32_t* d_sizes, uint32_t n,
                                          void* d_dst, size_t dst_cap, uint64_t* d_offsets, void* stream);
 
+/* ---- static-table training (reference: FPNG_TRAIN_HUFFMAN_TABLES, fpng_test -t; src/fpng.h:114-120) ----
+ * fpngb_train_accumulate_device: adds each image's 16-bit scaled symbol counts (what the reference accumulates in
+ *   g_huff_counts, src/fpng.cpp:751-755) to counts[288] (host); the histogram runs in the 2-pass histogram kernel.
+ * fpngb_create_dynamic_block_prefix: same outputs as fpng::create_dynamic_block_prefix (src/fpng.cpp:910-988).
+ * fpngb_set_static_table: installs such a prefix as the 1-pass table for `chans` (nbytes = 0 restores the built-in one). */
+FPNGB_API int fpngb_train_accumulate_device(const void* d_pixels, size_t image_stride, uint32_t n, uint32_t w, uint32_t h,
+                                            uint32_t chans, uint64_t* counts288, void* stream);
+FPNGB_API int fpngb_create_dynamic_block_prefix(const uint64_t* counts288, uint32_t chans, uint8_t* prefix, size_t prefix_cap,
+                                                size_t* prefix_len, uint64_t* bit_buf, int* bit_buf_size,
+                                                uint32_t* codes288, uint8_t* sizes288);
+FPNGB_API int fpngb_set_static_table(uint32_t chans, const uint8_t* prefix, size_t nbytes, uint32_t bit_buf, uint32_t bit_buf_size);
+
 /* Pinned host memory helpers for callers that want full PCIe bandwidth through the *_host entry points. */
 FPNGB_API void* fpngb_host_alloc(size_t bytes);
 FPNGB_API void fpngb_host_free(void* p);

@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libfpng_ref.so")
+REF_TRAIN_SO = os.path.join(HERE, "_ref", "libfpng_ref_train.so")
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -29,7 +30,8 @@ def build(force: bool = False) -> None:
     stale = (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src)
     ref_possible = os.path.exists("/root/reference/src/fpng.cpp")
     ref_stale = ref_possible and (
-        (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_shim.cpp")))
+        (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_shim.cpp"))
+        or (not os.path.exists(REF_TRAIN_SO)) or os.path.getmtime(REF_TRAIN_SO) < os.path.getmtime(os.path.join(HERE, "ref_train_shim.cpp")))
     if force or stale or ref_stale:
         subprocess.check_call(["make", "-s", "-f", os.path.join(HERE, "Makefile"), "all"], cwd=HERE)
 
@@ -220,3 +222,45 @@ class Ref:
         comp = self.L.ref_stb_decode(_ptr(a), a.size, _ptr(out), out.size, C.byref(ww), C.byref(hh), want_chans)
         px = out[: ww.value * hh.value * want_chans].copy() if comp else None
         return comp, px, ww.value, hh.value
+
+
+class RefTrainer:
+    """The reference built with FPNG_TRAIN_HUFFMAN_TABLES=1: g_huff_counts accumulation + create_dynamic_block_prefix."""
+
+    @staticmethod
+    def available() -> bool:
+        try:
+            build()
+        except Exception:
+            pass
+        return os.path.exists(REF_TRAIN_SO)
+
+    def __init__(self):
+        if not RefTrainer.available():
+            raise RuntimeError("oracle/_ref/libfpng_ref_train.so is not built")
+        L = C.CDLL(REF_TRAIN_SO)
+        L.reft_encode.restype = C.c_size_t
+        L.reft_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.reft_get_counts.argtypes = [C.c_void_p]
+        L.reft_create_prefix.restype = C.c_int
+        L.reft_create_prefix.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        L.reft_init()
+        self.L = L
+
+    def counts_from_encodes(self, images, w, h, chans):
+        self.L.reft_reset_counts()
+        for im in images:
+            a = _as_u8(im)
+            assert self.L.reft_encode(_ptr(a), w, h, chans, 1) > 0
+        out = np.zeros(288, np.uint64)
+        self.L.reft_get_counts(_ptr(out))
+        return out
+
+    def create_prefix(self, counts, chans):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        prefix = np.zeros(4096, np.uint8); n = C.c_size_t(); bb = C.c_uint64(); bs = C.c_int()
+        codes = np.zeros(288, np.uint32); sizes = np.zeros(288, np.uint8)
+        ok = self.L.reft_create_prefix(_ptr(counts), chans, _ptr(prefix), prefix.size, C.byref(n), C.byref(bb), C.byref(bs), _ptr(codes), _ptr(sizes))
+        assert ok
+        return prefix[: n.value].tobytes(), bb.value, bs.value, codes, sizes
