@@ -208,69 +208,67 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_hist16_kernel(ScanParams
 
 // ------------------------------------------------------------------------------------------------
 // K3 (v2): pack.  Every lane knows where its 16 pixels' tokens start (lane_ofs from the scan kernel), so it emits its
-// codes with a 64-bit accumulator straight into the warp's staging words: complete words with plain stores (they hold
-// only this lane's bits), its first word through a side slot and its last partial word with atomicOr.
+// codes through a 32-bit accumulator straight into the warp's staging words.  A staging word is COMPLETED (its bit 31
+// written) by exactly one lane, which stores it with a plain store; the bits other lanes own in that word (their last,
+// partial word) are OR-ed in after a warp barrier.  Nothing is re-zeroed between steps except the one word no lane
+// completes (the step's last, partial word), and lane 0 carries that word's bits into the next step in a register.
 // ------------------------------------------------------------------------------------------------
+// 32-bit shared-window addresses keep the stager's running pointer in ONE register (with a generic pointer the compiler
+// carried two copies and incremented both on every put)
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" :: "r"(saddr), "r"(v)); }
+__device__ __forceinline__ void reds_or_u32(uint32_t saddr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;\n" :: "r"(saddr), "r"(v)); }
+
 struct BitStager16 {
     uint32_t cur, n;            // word being filled (n < 32 valid bits)
-    uint32_t* dst;              // where `cur` goes once complete: the side slot for the lane's first word, staging afterwards
-    uint32_t* nxt;              // staging address of the word after `cur`
-    uint32_t* first_stage;      // staging address of the lane's first word
-    uint32_t* side;
-    __device__ __forceinline__ void begin(uint32_t* stage, uint32_t* side_slot, uint32_t bitpos)
+    uint32_t dst;               // shared-memory address of the staging word `cur` goes to
+    __device__ __forceinline__ void begin(uint32_t stage_saddr, uint32_t bitpos, uint32_t seed)
     {
-        cur = 0; n = bitpos & 31u; side = side_slot;
-        first_stage = stage + (bitpos >> 5); dst = side_slot; nxt = first_stage + 1;
+        cur = seed; n = bitpos & 31u; dst = stage_saddr + ((bitpos >> 5) << 2);
     }
-    // append `len` (<= 32 - with code < 2^len) bits
+    // append `len` (<= 32, code < 2^len) bits
     __device__ __forceinline__ void put(uint32_t code, uint32_t len)
     {
         const uint32_t lo = cur | (code << n);
-        const uint32_t hi = __funnelshift_l(code, 0u, n);               // bits that spill into the next word
+        const uint32_t hi = __funnelshift_l(code, 0u, n);               // bits that spill into the next word (0 when n == 0)
         const uint32_t n2 = n + len;
-        const bool f = n2 >= 32u;
-        if (f) *dst = lo;                                                // complete words hold only this lane's bits (or go to the side slot)
-        cur = f ? hi : lo;
+        if (n2 >= 32u) { sts_u32(dst, lo); dst += 4u; cur = hi; } else cur = lo;   // this lane owns bit 31 of the word: plain store
         n = n2 & 31u;
-        dst = f ? nxt : dst;
-        nxt += f ? 1 : 0;
     }
-    __device__ __forceinline__ void end()
-    {
-        if (dst == side) { if (cur) atomicOr(first_stage, cur); }        // everything fits in the first word
-        else {
-            atomicOr(first_stage, *side);
-            if (cur) atomicOr(dst, cur);
-        }
-    }
+    // after a warp barrier: the partial last word is shared with the next lane's first word
+    __device__ __forceinline__ void end() { if (cur) reds_or_u32(dst, cur); }
 };
+
+__device__ __forceinline__ void put_pair16(BitStager16& bs, uint32_t a, uint32_t b)   // two table entries (len << 16 | code), <= 24 bits
+{
+    const uint32_t la = a >> 16;
+    bs.put((a & 0xFFFFu) | ((b & 0xFFFFu) << la), la + (b >> 16));
+}
 
 template <int CHANS>
 __device__ __forceinline__ void put_literal16(BitStager16& bs, const uint32_t* s_lit, uint32_t px)
 {
-    const uint32_t c0 = s_lit[px & 0xFFu], c1 = s_lit[byte1(px)];
-    const uint32_t l0 = c0 >> 16, l1 = c1 >> 16;
-    const uint32_t lo = (c0 & 0xFFFFu) | ((c1 & 0xFFFFu) << l0);                 // <= 24 bits
-    bs.put(lo, l0 + l1);
-    if (CHANS == 4) {
-        const uint32_t c2 = s_lit[byte2(px)], c3 = s_lit[px >> 24];
-        const uint32_t l2 = c2 >> 16, l3 = c3 >> 16;
-        bs.put((c2 & 0xFFFFu) | ((c3 & 0xFFFFu) << l2), l2 + l3);
-    } else {
-        const uint32_t c2 = s_lit[px >> 16];
-        bs.put(c2 & 0xFFFFu, c2 >> 16);
-    }
+    put_pair16(bs, s_lit[px & 0xFFu], s_lit[byte1(px)]);
+    if (CHANS == 4) put_pair16(bs, s_lit[byte2(px)], s_lit[px >> 24]);
+    else { const uint32_t c2 = s_lit[px >> 16]; bs.put(c2 & 0xFFFFu, c2 >> 16); }
+}
+
+// the 4 literal codes of one 32-bit word of filtered bytes, in byte order, as two <= 24-bit puts
+__device__ __forceinline__ void put_word16(BitStager16& bs, const uint32_t* s_lit, uint32_t w)
+{
+    const uint32_t e0 = s_lit[w & 0xFFu], e1 = s_lit[byte1(w)], e2 = s_lit[byte2(w)], e3 = s_lit[w >> 24];
+    put_pair16(bs, e0, e1);
+    put_pair16(bs, e2, e3);
 }
 
 template <int CHANS>
 __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParams p)
 {
     constexpr uint32_t M = max_match_pixels(CHANS);
+    constexpr int kHalfWords = 2 * CHANS;        // filtered words of 8 pixels
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     uint32_t* s_lit = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * Walk16<CHANS>::kWarpBytes);
     uint32_t* s_match = s_lit + 256;
     uint32_t* s_stage_all = s_match + 88;
-    uint32_t* s_side_all = s_stage_all + kPack16Rows * stage16_words<CHANS>();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t img = blockIdx.y;
@@ -287,23 +285,23 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     }
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = book->lit[i];
     if (threadIdx.x < 88) s_match[threadIdx.x] = book->match[threadIdx.x];
-    for (uint32_t i = lane; i < (uint32_t)stage16_words<CHANS>(); i += 32) s_stage_all[warp * stage16_words<CHANS>() + i] = 0u;
     __syncthreads();
     if (y >= p.h) return;
 
     const uint32_t w = p.w, bpl = w * CHANS;
     const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
     const uint8_t* prev = y ? cur - bpl : nullptr;
-    uint32_t* file_words = reinterpret_cast<uint32_t*>(p.out + (size_t)img * p.out_stride);
     uint32_t* stage = s_stage_all + warp * stage16_words<CHANS>();
     uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
     const uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
     const uint32_t row_total = p.row_bits[(size_t)img * p.h + y];
     const unsigned long long G = p.row_ofs[(size_t)img * p.h + y];
-    const unsigned long long first_word = G >> 5;
-    unsigned long long gword = first_word;       // global word that stage[0] maps to
+    // global word that stage[0] maps to; advanced as words are flushed
+    uint32_t* gptr = reinterpret_cast<uint32_t*>(p.out + (size_t)img * p.out_stride) + (G >> 5);
+    bool first_pending = true;                   // the row's first word is shared with the previous row / the block header
     const uint32_t g31 = (uint32_t)(G & 31ull);
     uint32_t flushed_bits = 0;                   // row bits (incl. the G & 31 lead-in) already flushed to global, multiple of 32
+    uint32_t leftover = 0;                       // bits of the partially filled word carried from the previous step (lane 0 seeds with it)
     const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
     const uint32_t fcode = s_lit[y ? 2 : 0];
 
@@ -320,77 +318,67 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
         const uint32_t my_ofs = lane_ofs[step * 32u + lane];
         const uint32_t step_end = (step + 1 < nsteps) ? lane_ofs[(step + 1) * 32u] : row_total;   // row bits after this step
+        const uint32_t fill = g31 + step_end - flushed_bits;            // live bits in the staging buffer after this step
+        const uint32_t nwords = fill >> 5;
 
         BitStager16 bs;
-        uint32_t* side_slot = s_side_all + warp * 32 + lane;
+        const uint32_t stage_s = smem_u32(stage);
         // staging bit 0 corresponds to row bit (flushed_bits - g31); the filter literal sits at row bit 0
-        if (step == 0 && lane == 0) { bs.begin(stage, side_slot, g31); bs.put(fcode & 0xFFFFu, fcode >> 16); }
-        else bs.begin(stage, side_slot, g31 + my_ofs - flushed_bits);
-        // The 16 pixels are emitted in 4 groups of 4 by a ROLLED loop (the group's pixels are selected from registers):
-        // a fully unrolled body is ~80 KB of SASS and stalls on instruction fetch (ncu: no_instruction dominated).
+        if (lane == 0) {
+            stage[nwords] = 0u;                                          // the one word no lane completes in this step
+            if (step == 0) { bs.begin(stage_s, g31, 0u); bs.put(fcode & 0xFFFFu, fcode >> 16); }
+            else bs.begin(stage_s, g31 + my_ofs - flushed_bits, leftover);
+        } else bs.begin(stage_s, g31 + my_ofs - flushed_bits, 0u);
+        // The 16 pixels are emitted as 2 halves of 8 by a ROLLED loop (a fully unrolled body is ~80 KB of SASS and stalls
+        // on instruction fetch: ncu no_instruction dominated).
         uint32_t r = t.run;
 #pragma unroll 1
-        for (uint32_t g = 0; g < 4; g++) {
-            uint32_t q[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) q[j] = g == 0 ? px[j] : (g == 1 ? px[4 + j] : (g == 2 ? px[8 + j] : px[12 + j]));
-            // warp-uniform per group: all 128 pixels of this group (4 per lane) are literals
-            const bool all_lit = __all_sync(kFullMask, ((t.litm >> (4u * g)) & 15u) == 15u);
-            if (all_lit) {
-                // fast path (noisy rows): flush a match still pending from the previous group, then straight-line literals
+        for (uint32_t h = 0; h < 2; h++) {
+            // warp-uniform: all 256 pixels of this half (8 per lane) are literals
+            if (__all_sync(kFullMask, ((t.litm >> (8u * h)) & 0xFFu) == 0xFFu)) {
+                // fast path (noisy rows): flush a match still pending, then the half's filtered bytes in order, two codes per put
                 if (r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
-                if (CHANS == 3) {
-                    // 12 codes of 4 RGB pixels, appended two at a time (<= 24 bits per put): 6 puts instead of 8
-                    uint32_t e[12];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { e[3 * j] = s_lit[q[j] & 0xFFu]; e[3 * j + 1] = s_lit[byte1(q[j])]; e[3 * j + 2] = s_lit[q[j] >> 16]; }
-#pragma unroll
-                    for (int j = 0; j < 6; j++) {
-                        const uint32_t a = e[2 * j], b = e[2 * j + 1], la = a >> 16;
-                        bs.put((a & 0xFFFFu) | ((b & 0xFFFFu) << la), la + (b >> 16));
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) put_literal16<CHANS>(bs, s_lit, q[j]);
-                }
+                for (int j = 0; j < kHalfWords; j++) put_word16(bs, s_lit, h ? dw[kHalfWords + j] : dw[j]);
             } else {
-                const uint32_t e4 = t.eqm >> (4u * g);
+#pragma unroll 1
+                for (uint32_t g = 2u * h; g < 2u * h + 2u; g++) {
+                    uint32_t q[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (4u * g + j < t.nvp) {
-                        if (e4 & (1u << j)) {
-                            if (++r == M) { const uint32_t m = s_match[M]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
-                        } else {
-                            if (r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
-                            put_literal16<CHANS>(bs, s_lit, q[j]);
+                    for (int j = 0; j < 4; j++) q[j] = g == 0 ? px[j] : (g == 1 ? px[4 + j] : (g == 2 ? px[8 + j] : px[12 + j]));
+                    const uint32_t e4 = t.eqm >> (4u * g);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (4u * g + j < t.nvp) {
+                            if (e4 & (1u << j)) {
+                                if (++r == M) { const uint32_t m = s_match[M]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
+                            } else {
+                                if (r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
+                                put_literal16<CHANS>(bs, s_lit, q[j]);
+                            }
                         }
                     }
                 }
             }
         }
         if (t.last && r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); }
-        bs.end();
+        __syncwarp();                                                    // all complete words are stored ...
+        bs.end();                                                        // ... before the partial ones are OR-ed in
         __syncwarp();
 
-        // ---- flush whole words; the row's first word is shared with the previous row / the block header
-        const uint32_t fill = g31 + step_end - flushed_bits;            // live bits in the staging buffer
-        const uint32_t nwords = fill >> 5;
-        const uint32_t leftover = stage[nwords];
+        // ---- flush the complete words; carry the partial one in a register
+        leftover = stage[nwords];
         for (uint32_t j = lane; j < nwords; j += 32) {
             const uint32_t v = stage[j];
-            if (gword + j == first_word) atomicOr(&file_words[gword + j], v);
-            else file_words[gword + j] = v;
+            if (first_pending && j == 0) atomicOr(gptr, v);
+            else gptr[j] = v;
         }
-        __syncwarp();
-        for (uint32_t j = lane; j <= nwords; j += 32) stage[j] = (j == 0) ? leftover : 0u;
-        __syncwarp();
-        gword += nwords;
+        __syncwarp();                                                    // staging is rewritten by the next step
+        if (nwords) first_pending = false;
+        gptr += nwords;
         flushed_bits += nwords << 5;
     }
-    if (lane == 0) {
-        const uint32_t v = stage[0];
-        if (v) atomicOr(&file_words[gword], v);
-    }
+    if (lane == 0 && leftover) atomicOr(gptr, leftover);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -403,7 +391,7 @@ bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t
 }
 
 template <int CHANS> constexpr size_t scan16_smem() { return kScan16Rows * Walk16<CHANS>::kWarpBytes + 256 + 96; }
-template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk16<CHANS>::kWarpBytes + (256 + 88 + kPack16Rows * stage16_words<CHANS>() + kPack16Rows * 32) * 4; }
+template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk16<CHANS>::kWarpBytes + (256 + 88 + kPack16Rows * stage16_words<CHANS>()) * 4; }
 
 // opt in to > 48 KiB of dynamic shared memory (per kernel instantiation, once per process)
 #define FPNGB_SET_SMEM(kernel, bytes) do { static bool done_ = false; \
