@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
     const uint32_t filt = y ? 2u : 0u;
     const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
     uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
-    uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
+    uint2* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
 
     Walk16<CHANS> wk; wk.init(lane, tiles);
     RowCarry carry = {0u, 0u};
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
         // bit offset of this lane's first token inside the row (the pack kernel starts writing there)
         uint32_t step_bits;
         const uint32_t ex = warp_excl_scan_u32(bits, lane, step_bits);
-        lane_ofs[step * 32u + lane] = row_run + ex;
+        lane_ofs[step * 32u + lane] = make_uint2(row_run + ex, lane_info16(t));     // the pack kernel starts from these instead of re-classifying
         row_run += step_bits;
     }
 
@@ -207,16 +207,18 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_hist16_kernel(ScanParams
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3 (v2): pack.  Every lane knows where its 16 pixels' tokens start (lane_ofs from the scan kernel), so it emits its
-// codes through a 32-bit accumulator straight into the warp's staging words.  A staging word is COMPLETED (its bit 31
-// written) by exactly one lane, which stores it with a plain store; the bits other lanes own in that word (their last,
-// partial word) are OR-ed in after a warp barrier.  Nothing is re-zeroed between steps except the one word no lane
-// completes (the step's last, partial word), and lane 0 carries that word's bits into the next step in a register.
+// K3 (v2): pack.  Every lane knows where its 16 pixels' tokens start and how they classify (lane_ofs from the scan
+// kernel: bit offset + lane_info16), so it emits its codes through a 32-bit accumulator straight into the warp's staging
+// words.  A staging word is COMPLETED (its bit 31 written) by exactly one lane, which stores it with a plain store; the
+// bits other lanes own in that word (their last, partial word) are OR-ed in after a warp barrier.  Nothing is re-zeroed
+// between steps except the one word no lane completes (the step's last, partial word), and lane 0 carries that word's
+// bits into the next step in a register.
 // ------------------------------------------------------------------------------------------------
 // 32-bit shared-window addresses keep the stager's running pointer in ONE register (with a generic pointer the compiler
 // carried two copies and incremented both on every put)
 __device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" :: "r"(saddr), "r"(v)); }
 __device__ __forceinline__ void reds_or_u32(uint32_t saddr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;\n" :: "r"(saddr), "r"(v)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr)); return v; }
 
 struct BitStager16 {
     uint32_t cur, n;            // word being filled (n < 32 valid bits)
@@ -225,7 +227,7 @@ struct BitStager16 {
     {
         cur = seed; n = bitpos & 31u; dst = stage_saddr + ((bitpos >> 5) << 2);
     }
-    // append `len` (<= 32, code < 2^len) bits
+    // append `len` (<= 32, code < 2^len) bits; len == 0 (code == 0) is a no-op
     __device__ __forceinline__ void put(uint32_t code, uint32_t len)
     {
         const uint32_t lo = cur | (code << n);
@@ -243,21 +245,60 @@ __device__ __forceinline__ void put_pair16(BitStager16& bs, uint32_t a, uint32_t
     const uint32_t la = a >> 16;
     bs.put((a & 0xFFFFu) | ((b & 0xFFFFu) << la), la + (b >> 16));
 }
+__device__ __forceinline__ void put_match16(BitStager16& bs, uint32_t s_match_saddr, uint32_t r)
+{
+    const uint32_t m = lds_u32(s_match_saddr + r * 4u);
+    bs.put(m & 0xFFFFFFu, m >> 24);
+}
+
+// byte offset of the literal-table entry of byte POS of word w, OR-ed with `nb` (0, or 0x400 = the all-zero upper half of
+// the table: a "null" entry of 0 bits, used to switch a pixel's literals off without a branch)
+template <int POS>
+__device__ __forceinline__ uint32_t lit_off16(uint32_t w, uint32_t nb)
+{
+    const uint32_t x = POS == 0 ? (w << 2) : (POS == 1 ? (w >> 6) : (POS == 2 ? (w >> 14) : (w >> 22)));
+    return (x & 0x3FCu) | nb;                                            // one LOP3
+}
 
 template <int CHANS>
-__device__ __forceinline__ void put_literal16(BitStager16& bs, const uint32_t* s_lit, uint32_t px)
+__device__ __forceinline__ void put_literal16(BitStager16& bs, uint32_t s_lit_saddr, uint32_t px)
 {
-    put_pair16(bs, s_lit[px & 0xFFu], s_lit[byte1(px)]);
-    if (CHANS == 4) put_pair16(bs, s_lit[byte2(px)], s_lit[px >> 24]);
-    else { const uint32_t c2 = s_lit[px >> 16]; bs.put(c2 & 0xFFFFu, c2 >> 16); }
+    put_pair16(bs, lds_u32(s_lit_saddr + lit_off16<0>(px, 0u)), lds_u32(s_lit_saddr + lit_off16<1>(px, 0u)));
+    if (CHANS == 4) put_pair16(bs, lds_u32(s_lit_saddr + lit_off16<2>(px, 0u)), lds_u32(s_lit_saddr + lit_off16<3>(px, 0u)));
+    else { const uint32_t c2 = lds_u32(s_lit_saddr + lit_off16<2>(px, 0u)); bs.put(c2 & 0xFFFFu, c2 >> 16); }
 }
 
 // the 4 literal codes of one 32-bit word of filtered bytes, in byte order, as two <= 24-bit puts
-__device__ __forceinline__ void put_word16(BitStager16& bs, const uint32_t* s_lit, uint32_t w)
+__device__ __forceinline__ void put_word16(BitStager16& bs, uint32_t s_lit_saddr, uint32_t w, uint32_t nb)
 {
-    const uint32_t e0 = s_lit[w & 0xFFu], e1 = s_lit[byte1(w)], e2 = s_lit[byte2(w)], e3 = s_lit[w >> 24];
+    const uint32_t e0 = lds_u32(s_lit_saddr + lit_off16<0>(w, nb)), e1 = lds_u32(s_lit_saddr + lit_off16<1>(w, nb));
+    const uint32_t e2 = lds_u32(s_lit_saddr + lit_off16<2>(w, nb)), e3 = lds_u32(s_lit_saddr + lit_off16<3>(w, nb));
     put_pair16(bs, e0, e1);
     put_pair16(bs, e2, e3);
+}
+
+// entry of byte B (0..23) of a half's 6 RGB words
+template <int B>
+__device__ __forceinline__ uint32_t lit_entry_rgb16(uint32_t s_lit_saddr, const uint32_t (&hw)[6], uint32_t nb)
+{
+    return lds_u32(s_lit_saddr + lit_off16<B & 3>(hw[B >> 2], nb));
+}
+
+// pending run length before pixel kk (0..16) of a lane, from its equality mask and the run entering the lane
+template <uint32_t M>
+__device__ __forceinline__ uint32_t run_before16(uint32_t eqm, uint32_t r_in, uint32_t kk)
+{
+    const uint32_t t = ~eqm & ((1u << kk) - 1u);                         // non-match pixels below kk
+    if (t == 0u) { const uint32_t r = kk + r_in; return r >= M ? r - M : r; }
+    return kk - 1u - (31u - (uint32_t)__clz((int)t));
+}
+
+// a token event at pixel kk: the run reaches M at this (match) pixel, or a pending run is flushed before this literal
+template <uint32_t M>
+__device__ __forceinline__ void put_event16(BitStager16& bs, uint32_t s_match_saddr, uint32_t eqm, uint32_t r_in, uint32_t kk)
+{
+    const uint32_t len = ((eqm >> kk) & 1u) ? M : run_before16<M>(eqm, r_in, kk);
+    if (len) put_match16(bs, s_match_saddr, len);
 }
 
 template <int CHANS>
@@ -266,8 +307,8 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     constexpr uint32_t M = max_match_pixels(CHANS);
     constexpr int kHalfWords = 2 * CHANS;        // filtered words of 8 pixels
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    uint32_t* s_lit = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * Walk16<CHANS>::kWarpBytes);
-    uint32_t* s_match = s_lit + 256;
+    uint32_t* s_lit = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * Walk16<CHANS>::kWarpBytes);   // [512]: 256 entries + 256 zeros
+    uint32_t* s_match = s_lit + 512;
     uint32_t* s_stage_all = s_match + 88;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -283,7 +324,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         }
         return;
     }
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = book->lit[i];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_lit[i] = book->lit[i]; s_lit[256 + i] = 0u; }
     if (threadIdx.x < 88) s_match[threadIdx.x] = book->match[threadIdx.x];
     __syncthreads();
     if (y >= p.h) return;
@@ -292,8 +333,9 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
     const uint8_t* prev = y ? cur - bpl : nullptr;
     uint32_t* stage = s_stage_all + warp * stage16_words<CHANS>();
+    const uint32_t stage_s = smem_u32(stage), lit_s = smem_u32(s_lit), match_s = smem_u32(s_match);
     uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
-    const uint32_t* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
+    const uint2* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
     const uint32_t row_total = p.row_bits[(size_t)img * p.h + y];
     const unsigned long long G = p.row_ofs[(size_t)img * p.h + y];
     // global word that stage[0] maps to; advanced as words are flushed
@@ -306,23 +348,28 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     const uint32_t fcode = s_lit[y ? 2 : 0];
 
     Walk16<CHANS> wk; wk.init(lane, tiles);
-    RowCarry carry = {0u, 0u};
     uint32_t dummyA = 0; unsigned long long dummyB = 0;
     wk.prefetch(cur, prev, 0, bpl, lane, tiles);
+    uint2 mine = lane_ofs[lane];
     for (uint32_t step = 0; step < nsteps; step++) {
-        uint32_t dw[Walk16<CHANS>::kWords], px[16];
+        uint32_t dw[Walk16<CHANS>::kWords];
         wk.template consume<false>(prev != nullptr, step, bpl, lane, tiles, dw, dummyA, dummyB);
-        if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);         // lands while this step is emitted
-        Walk16<CHANS>::pixels(dw, px);
-        const uint32_t p0 = step * kStep16 + lane * kPix16;
-        const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
-        const uint32_t my_ofs = lane_ofs[step * 32u + lane];
-        const uint32_t step_end = (step + 1 < nsteps) ? lane_ofs[(step + 1) * 32u] : row_total;   // row bits after this step
+        const bool more = step + 1 < nsteps;
+        if (more) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);                      // lands while this step is emitted
+        const uint32_t my_ofs = mine.x, info = mine.y;
+        if (more) mine = lane_ofs[(step + 1) * 32u + lane];
+        const uint32_t step_end = more ? __shfl_sync(kFullMask, mine.x, 0) : row_total;    // row bits after this step
         const uint32_t fill = g31 + step_end - flushed_bits;            // live bits in the staging buffer after this step
         const uint32_t nwords = fill >> 5;
+        // classification of this lane's 16 pixels, as computed by the scan kernel
+        const uint32_t eqm = info & 0xFFFFu, r_in = (info >> 16) & 0x7Fu, nvp = (info >> 23) & 0x1Fu;
+        const uint32_t litm = ((1u << nvp) - 1u) & ~eqm;
+        // token events: a pending run flushed before a literal pixel, or the run reaching M at a match pixel (at most one per lane)
+        const uint32_t lead = (uint32_t)__ffs((int)~eqm) - 1u;          // leading match pixels (<= 16)
+        const uint32_t kM = M - 1u - r_in;
+        const uint32_t evm = (litm & ((eqm << 1) | (r_in ? 1u : 0u))) | (kM < lead ? (1u << kM) : 0u);
 
         BitStager16 bs;
-        const uint32_t stage_s = smem_u32(stage);
         // staging bit 0 corresponds to row bit (flushed_bits - g31); the filter literal sits at row bit 0
         if (lane == 0) {
             stage[nwords] = 0u;                                          // the one word no lane completes in this step
@@ -330,38 +377,83 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
             else bs.begin(stage_s, g31 + my_ofs - flushed_bits, leftover);
         } else bs.begin(stage_s, g31 + my_ofs - flushed_bits, 0u);
         // The 16 pixels are emitted as 2 halves of 8 by a ROLLED loop (a fully unrolled body is ~80 KB of SASS and stalls
-        // on instruction fetch: ncu no_instruction dominated).
-        uint32_t r = t.run;
+        // on instruction fetch: ncu no_instruction dominated).  Per half one of four warp-uniform paths:
 #pragma unroll 1
         for (uint32_t h = 0; h < 2; h++) {
-            // warp-uniform: all 256 pixels of this half (8 per lane) are literals
-            if (__all_sync(kFullMask, ((t.litm >> (8u * h)) & 0xFFu) == 0xFFu)) {
-                // fast path (noisy rows): flush a match still pending, then the half's filtered bytes in order, two codes per put
-                if (r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
+            const uint32_t lit8 = (litm >> (8u * h)) & 0xFFu, ev8 = (evm >> (8u * h)) & 0xFFu;
+            uint32_t hw[kHalfWords];
 #pragma unroll
-                for (int j = 0; j < kHalfWords; j++) put_word16(bs, s_lit, h ? dw[kHalfWords + j] : dw[j]);
+            for (int j = 0; j < kHalfWords; j++) hw[j] = h ? dw[kHalfWords + j] : dw[j];
+            if (__all_sync(kFullMask, lit8 == 0xFFu && ev8 == 0u)) {
+                // (1) all 256 pixels are literals, no run pending (noisy rows): the filtered bytes in order, two codes per put
+#pragma unroll
+                for (int j = 0; j < kHalfWords; j++) put_word16(bs, lit_s, hw[j], 0u);
+            } else if (__all_sync(kFullMask, lit8 == 0u)) {
+                // (2) no literal at all (inside long runs): only a run reaching M emits a token
+                if (ev8) put_match16(bs, match_s, M);
+            } else if (__reduce_add_sync(kFullMask, (uint32_t)__popc(lit8)) >= 16u) {
+                // (3) mixed: straight-line literal emission for every pixel, switched off per pixel through the table's null
+                //     half; the rare run tokens are inserted by a per-pixel event check
+                const uint32_t nl = ~lit8;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (ev8 & (1u << k)) put_event16<M>(bs, match_s, eqm, r_in, 8u * h + k);
+                    const uint32_t nb = (k <= 10 ? (nl << (10 - k)) : (nl >> (k - 10))) & 0x400u;
+                    if (CHANS == 4) put_word16(bs, lit_s, hw[k], nb);
+                    else {
+                        uint32_t e0, e1, e2;
+                        // bytes 3k .. 3k+2 of the half's 24 filtered bytes
+                        const uint32_t* hp = hw;
+                        switch (k) {                                     // compile-time after unrolling
+                        default:
+                        case 0: e0 = lds_u32(lit_s + lit_off16<0>(hp[0], nb)); e1 = lds_u32(lit_s + lit_off16<1>(hp[0], nb)); e2 = lds_u32(lit_s + lit_off16<2>(hp[0], nb)); break;
+                        case 1: e0 = lds_u32(lit_s + lit_off16<3>(hp[0], nb)); e1 = lds_u32(lit_s + lit_off16<0>(hp[1], nb)); e2 = lds_u32(lit_s + lit_off16<1>(hp[1], nb)); break;
+                        case 2: e0 = lds_u32(lit_s + lit_off16<2>(hp[1], nb)); e1 = lds_u32(lit_s + lit_off16<3>(hp[1], nb)); e2 = lds_u32(lit_s + lit_off16<0>(hp[2], nb)); break;
+                        case 3: e0 = lds_u32(lit_s + lit_off16<1>(hp[2], nb)); e1 = lds_u32(lit_s + lit_off16<2>(hp[2], nb)); e2 = lds_u32(lit_s + lit_off16<3>(hp[2], nb)); break;
+                        case 4: e0 = lds_u32(lit_s + lit_off16<0>(hp[3], nb)); e1 = lds_u32(lit_s + lit_off16<1>(hp[3], nb)); e2 = lds_u32(lit_s + lit_off16<2>(hp[3], nb)); break;
+                        case 5: e0 = lds_u32(lit_s + lit_off16<3>(hp[3], nb)); e1 = lds_u32(lit_s + lit_off16<0>(hp[4], nb)); e2 = lds_u32(lit_s + lit_off16<1>(hp[4], nb)); break;
+                        case 6: e0 = lds_u32(lit_s + lit_off16<2>(hp[4], nb)); e1 = lds_u32(lit_s + lit_off16<3>(hp[4], nb)); e2 = lds_u32(lit_s + lit_off16<0>(hp[5], nb)); break;
+                        case 7: e0 = lds_u32(lit_s + lit_off16<1>(hp[5], nb)); e1 = lds_u32(lit_s + lit_off16<2>(hp[5], nb)); e2 = lds_u32(lit_s + lit_off16<3>(hp[5], nb)); break;
+                        }
+                        put_pair16(bs, e0, e1);
+                        bs.put(e2 & 0xFFFFu, e2 >> 16);
+                    }
+                }
             } else {
+                // (4) sparse literals (RLE-dominated rows): per-pixel token walk, 4 pixels at a time
+                uint32_t r = run_before16<M>(eqm, r_in, 8u * h);
 #pragma unroll 1
-                for (uint32_t g = 2u * h; g < 2u * h + 2u; g++) {
+                for (uint32_t g = 0; g < 2; g++) {
                     uint32_t q[4];
+                    if (CHANS == 4) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) q[j] = g == 0 ? px[j] : (g == 1 ? px[4 + j] : (g == 2 ? px[8 + j] : px[12 + j]));
-                    const uint32_t e4 = t.eqm >> (4u * g);
+                        for (int j = 0; j < 4; j++) q[j] = g ? hw[4 + j] : hw[j];
+                    } else {
+                        const uint32_t w0 = g ? hw[3] : hw[0], w1 = g ? hw[4] : hw[1], w2 = g ? hw[5] : hw[2];
+                        q[0] = w0 & 0x00FFFFFFu;
+                        q[1] = __byte_perm(w0, w1, 0x4543) & 0x00FFFFFFu;
+                        q[2] = __byte_perm(w1, w2, 0x4432) & 0x00FFFFFFu;
+                        q[3] = w2 >> 8;
+                    }
+                    const uint32_t e4 = eqm >> (8u * h + 4u * g), base = 8u * h + 4u * g;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        if (4u * g + j < t.nvp) {
+                        if (base + j < nvp) {
                             if (e4 & (1u << j)) {
-                                if (++r == M) { const uint32_t m = s_match[M]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
+                                if (++r == M) { put_match16(bs, match_s, M); r = 0; }
                             } else {
-                                if (r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); r = 0; }
-                                put_literal16<CHANS>(bs, s_lit, q[j]);
+                                if (r) { put_match16(bs, match_s, r); r = 0; }
+                                put_literal16<CHANS>(bs, lit_s, q[j]);
                             }
                         }
                     }
                 }
             }
         }
-        if (t.last && r) { const uint32_t m = s_match[r]; bs.put(m & 0xFFFFFFu, m >> 24); }
+        if (info >> 28) {                                                // this lane holds the scanline's last pixel: flush the trailing run
+            const uint32_t r = run_before16<M>(eqm, r_in, nvp);
+            if (r) put_match16(bs, match_s, r);
+        }
         __syncwarp();                                                    // all complete words are stored ...
         bs.end();                                                        // ... before the partial ones are OR-ed in
         __syncwarp();
@@ -391,7 +483,7 @@ bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t
 }
 
 template <int CHANS> constexpr size_t scan16_smem() { return kScan16Rows * Walk16<CHANS>::kWarpBytes + 256 + 96; }
-template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk16<CHANS>::kWarpBytes + (256 + 88 + kPack16Rows * stage16_words<CHANS>()) * 4; }
+template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk16<CHANS>::kWarpBytes + (512 + 88 + kPack16Rows * stage16_words<CHANS>()) * 4; }
 
 // opt in to > 48 KiB of dynamic shared memory (per kernel instantiation, once per process)
 #define FPNGB_SET_SMEM(kernel, bytes) do { static bool done_ = false; \

@@ -160,14 +160,14 @@ static void prof_mark(ProfSet* ps, int slot, cudaStream_t s)
 
 struct Workspace {
     uint32_t* row_bits; uint2* row_adler; unsigned long long* row_ofs; ImageState* st; uint32_t* hist; CodeBook* books;
-    uint32_t* lane_ofs; uint32_t lane_ofs_pitch;
+    uint2* lane_ofs; uint32_t lane_ofs_pitch;
 };
 
 
 static int carve_workspace(Context& c, uint32_t n, uint32_t h, uint32_t width, bool two_pass, Workspace& w)
 {
     const size_t rows = (size_t)n * h;
-    const uint32_t lane_pitch = ((width + 511u) / 512u) * 32u;       // one u32 per 16-pixel group, whole warp steps
+    const uint32_t lane_pitch = ((width + 511u) / 512u) * 32u;       // one uint2 per 16-pixel group, whole warp steps
     size_t o = 0;
     const size_t o_bits = o; o = align_up(o + rows * 4, 256);
     const size_t o_adl = o; o = align_up(o + rows * 8, 256);
@@ -175,13 +175,13 @@ static int carve_workspace(Context& c, uint32_t n, uint32_t h, uint32_t width, b
     const size_t o_st = o; o = align_up(o + (size_t)n * sizeof(ImageState), 256);
     const size_t o_hist = o; o = align_up(o + (two_pass ? (size_t)n * 288 * 4 : 0), 256);
     const size_t o_books = o; o = align_up(o + (two_pass ? (size_t)n * sizeof(CodeBook) : 0), 256);
-    const size_t o_lane = o; o = align_up(o + rows * lane_pitch * 4, 256);
+    const size_t o_lane = o; o = align_up(o + rows * lane_pitch * 8, 256);
     int rc = c.ws.reserve(o);
     if (rc) return rc;
     uint8_t* b = (uint8_t*)c.ws.p;
     w.row_bits = (uint32_t*)(b + o_bits); w.row_adler = (uint2*)(b + o_adl); w.row_ofs = (unsigned long long*)(b + o_ofs);
     w.st = (ImageState*)(b + o_st); w.hist = (uint32_t*)(b + o_hist); w.books = (CodeBook*)(b + o_books);
-    w.lane_ofs = (uint32_t*)(b + o_lane); w.lane_ofs_pitch = lane_pitch;
+    w.lane_ofs = (uint2*)(b + o_lane); w.lane_ofs_pitch = lane_pitch;
     return 0;
 }
 

@@ -19,7 +19,7 @@ struct ScanParams {
     ImageState* st;                               // [n]
     uint32_t* hist;                               // [n*288] (histogram mode)
     uint32_t merge_first_unit;                    // RGB 1-pass: filter literal and pixel 0 share a flush unit (fpng.cpp:1187-1203)
-    uint32_t* lane_ofs; uint32_t lane_ofs_pitch;  // v2 kernels: [n*h][pitch] bit offset of every 16-pixel group inside its row
+    uint2* lane_ofs; uint32_t lane_ofs_pitch;     // v2 kernels: [n*h][pitch] per 16-pixel group: .x bit offset inside its row, .y lane_info16()
 };
 
 struct OffsetsParams {
@@ -37,7 +37,7 @@ struct PackParams {
     const CodeBook* books; uint32_t book_stride;
     const unsigned long long* row_ofs;
     const uint32_t* row_bits;                     // v2 kernels: total token bits per row
-    const uint32_t* lane_ofs; uint32_t lane_ofs_pitch;
+    const uint2* lane_ofs; uint32_t lane_ofs_pitch;
     uint2* row_adler;                             // rewritten for stored images (raw bytes, filter 0)
     const ImageState* st;
     uint8_t* out; size_t out_stride;

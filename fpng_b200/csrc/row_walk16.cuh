@@ -224,6 +224,9 @@ struct Lane16 {
     bool last;         // this lane holds the scanline's last pixel
 };
 
+// what the scan kernel hands to the pack kernel per lane and step: eqm | run << 16 | nvp << 23 | last << 28
+__device__ __forceinline__ uint32_t lane_info16(const Lane16& t) { return t.eqm | (t.run << 16) | (t.nvp << 23) | (t.last ? (1u << 28) : 0u); }
+
 template <int CHANS>
 __device__ __forceinline__ Lane16 classify16(const uint32_t (&px)[16], uint32_t p0, uint32_t w, RowCarry& carry, uint32_t lane)
 {
