@@ -8,6 +8,8 @@ namespace fpngb {
 
 constexpr int kScan16Rows = 8;                   // warps (scanlines) per CTA, scan
 constexpr int kPack16Rows = 4;                   // warps per CTA, pack (larger staging buffers)
+constexpr int kPack16RowsPerWarp = 5;            // consecutive scanlines per warp, pack: amortises the CTA prologue and lets the first tile of
+                                                 // a scanline be prefetched during the previous scanline's last step
 // staging words per warp step: lead-in (31) + filter literal (12) + 512 pixel slots of [pending match 18 bits][literal 12*CHANS bits]
 template <int CHANS> __host__ __device__ constexpr int stage16_words() { return ((31 + 12 + 512 * (18 + 12 * CHANS)) / 32 + 1 + 15) / 16 * 16; }
 
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
     wk.prefetch(cur, prev, 0, bpl, lane, tiles);
     for (uint32_t step = 0; step < nsteps; step++) {
         uint32_t dw[Walk16<CHANS>::kWords], px[16];
-        wk.template consume<true>(prev != nullptr, step, bpl, lane, tiles, dw, sumA, sumB);
+        wk.template consume<true>(prev != nullptr, step, step, bpl, lane, tiles, dw, sumA, sumB);
         if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);         // lands while this step is processed
         Walk16<CHANS>::pixels(dw, px);
         const uint32_t p0 = step * kStep16 + lane * kPix16;
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_hist16_kernel(ScanParams
         wk.prefetch(cur, prev, 0, bpl, lane, tiles);
         for (uint32_t step = 0; step < nsteps; step++) {
             uint32_t dw[Walk16<CHANS>::kWords], px[16];
-            wk.template consume<false>(prev != nullptr, step, bpl, lane, tiles, dw, dummyA, dummyB);
+            wk.template consume<false>(prev != nullptr, step, step, bpl, lane, tiles, dw, dummyA, dummyB);
             if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);
             Walk16<CHANS>::pixels(dw, px);
             const uint32_t p0 = step * kStep16 + lane * kPix16;
@@ -313,54 +315,69 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t img = blockIdx.y;
-    const uint32_t y = blockIdx.x * kPack16Rows + warp;
+    const uint32_t row0 = (blockIdx.x * kPack16Rows + warp) * kPack16RowsPerWarp;      // this warp's first scanline
     const CodeBook* book = p.books + (size_t)img * p.book_stride;
     const ImageState st = p.st[img];
-    if (st.stored) {                             // stored-block fallback (fpng.cpp:818-866): strided copy of this row
-        if (y < p.h) {
-            const uint32_t bpl_s = p.w * CHANS;
+    if (st.stored) {                             // stored-block fallback (fpng.cpp:818-866): strided copy of the rows
+        const uint32_t bpl_s = p.w * CHANS;
+        for (uint32_t y = row0; y < min(row0 + kPack16RowsPerWarp, p.h); y++)
             store_row_raw(p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl_s, p.out + (size_t)img * p.out_stride + kPngHeaderSize,
                           y, bpl_s, lane, &p.row_adler[(size_t)img * p.h + y]);
-        }
         return;
     }
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_lit[i] = book->lit[i]; s_lit[256 + i] = 0u; }
     if (threadIdx.x < 88) s_match[threadIdx.x] = book->match[threadIdx.x];
     __syncthreads();
-    if (y >= p.h) return;
+    if (row0 >= p.h) return;
 
     const uint32_t w = p.w, bpl = w * CHANS;
-    const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
-    const uint8_t* prev = y ? cur - bpl : nullptr;
+    const uint32_t nrows = min((uint32_t)kPack16RowsPerWarp, p.h - row0);
+    const uint8_t* img_px = p.pixels + (size_t)img * p.image_stride;
     uint32_t* stage = s_stage_all + warp * stage16_words<CHANS>();
     const uint32_t stage_s = smem_u32(stage), lit_s = smem_u32(s_lit), match_s = smem_u32(s_match);
     uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
-    const uint2* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
-    const uint32_t row_total = p.row_bits[(size_t)img * p.h + y];
-    const unsigned long long G = p.row_ofs[(size_t)img * p.h + y];
-    // global word that stage[0] maps to; advanced as words are flushed
-    uint32_t* gptr = reinterpret_cast<uint32_t*>(p.out + (size_t)img * p.out_stride) + (G >> 5);
+    const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
+    const uint32_t nitems = nrows * nsteps;      // (scanline, step) work items of this warp, walked as one pipelined sequence
+    // per-row constants of all this warp's rows, one row per lane (broadcast at the row's first step)
+    const size_t ridx0 = (size_t)img * p.h + row0;
+    const unsigned long long my_G = lane < nrows ? p.row_ofs[ridx0 + lane] : 0ull;
+    const uint32_t my_total = lane < nrows ? p.row_bits[ridx0 + lane] : 0u;
+    const uint2* lane_ofs = p.lane_ofs + ridx0 * p.lane_ofs_pitch + lane;              // this lane's entry of (row0, step 0)
+
+    uint32_t* gptr = nullptr;                    // global word that stage[0] maps to; advanced as words are flushed
     bool first_pending = true;                   // the row's first word is shared with the previous row / the block header
-    const uint32_t g31 = (uint32_t)(G & 31ull);
+    uint32_t g31 = 0, row_total = 0;
     uint32_t flushed_bits = 0;                   // row bits (incl. the G & 31 lead-in) already flushed to global, multiple of 32
     uint32_t leftover = 0;                       // bits of the partially filled word carried from the previous step (lane 0 seeds with it)
-    const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
-    const uint32_t fcode = s_lit[y ? 2 : 0];
 
     Walk16<CHANS> wk; wk.init(lane, tiles);
     uint32_t dummyA = 0; unsigned long long dummyB = 0;
-    wk.prefetch(cur, prev, 0, bpl, lane, tiles);
-    uint2 mine = lane_ofs[lane];
-    for (uint32_t step = 0; step < nsteps; step++) {
+    {
+        const uint8_t* c0 = img_px + (size_t)row0 * bpl;
+        wk.prefetch(c0, row0 ? c0 - bpl : nullptr, 0, bpl, lane, tiles);
+    }
+    uint2 mine = lane_ofs[0];
+    uint32_t r_i = 0, step = 0;                  // row (relative to row0) and step of the current item
+    for (uint32_t item = 0; item < nitems; item++) {
+        const uint32_t y = row0 + r_i;
+        if (step == 0) {
+            const unsigned long long G = __shfl_sync(kFullMask, my_G, r_i);
+            row_total = __shfl_sync(kFullMask, my_total, r_i);
+            gptr = reinterpret_cast<uint32_t*>(p.out + (size_t)img * p.out_stride) + (G >> 5);
+            g31 = (uint32_t)(G & 31ull);
+            first_pending = true; flushed_bits = 0; leftover = 0;
+        }
         uint32_t dw[Walk16<CHANS>::kWords];
-        wk.template consume<false>(prev != nullptr, step, bpl, lane, tiles, dw, dummyA, dummyB);
-        const bool more = step + 1 < nsteps;
-        if (more) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);                      // lands while this step is emitted
+        wk.template consume<false>(y != 0, item, step, bpl, lane, tiles, dw, dummyA, dummyB);
+        // the next item (possibly the first step of the next scanline) is fetched while this one is emitted
+        const bool more = step + 1 < nsteps;     // more steps in this row
         const uint32_t my_ofs = mine.x, info = mine.y;
-        if (more) mine = lane_ofs[(step + 1) * 32u + lane];
-        const uint32_t step_end = more ? __shfl_sync(kFullMask, mine.x, 0) : row_total;    // row bits after this step
-        const uint32_t fill = g31 + step_end - flushed_bits;            // live bits in the staging buffer after this step
-        const uint32_t nwords = fill >> 5;
+        if (item + 1 < nitems) {
+            const uint32_t ny = more ? y : y + 1, nstep = more ? step + 1 : 0;
+            const uint8_t* nc = img_px + (size_t)ny * bpl;
+            wk.prefetch(nc, ny ? nc - bpl : nullptr, nstep, bpl, lane, tiles);
+            mine = lane_ofs[(size_t)(ny - row0) * p.lane_ofs_pitch + nstep * 32u];
+        }
         // classification of this lane's 16 pixels, as computed by the scan kernel
         const uint32_t eqm = info & 0xFFFFu, r_in = (info >> 16) & 0x7Fu, nvp = (info >> 23) & 0x1Fu;
         const uint32_t litm = ((1u << nvp) - 1u) & ~eqm;
@@ -372,8 +389,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         BitStager16 bs;
         // staging bit 0 corresponds to row bit (flushed_bits - g31); the filter literal sits at row bit 0
         if (lane == 0) {
-            stage[nwords] = 0u;                                          // the one word no lane completes in this step
-            if (step == 0) { bs.begin(stage_s, g31, 0u); bs.put(fcode & 0xFFFFu, fcode >> 16); }
+            if (step == 0) { const uint32_t fcode = s_lit[y ? 2 : 0]; bs.begin(stage_s, g31, 0u); bs.put(fcode & 0xFFFFu, fcode >> 16); }
             else bs.begin(stage_s, g31 + my_ofs - flushed_bits, leftover);
         } else bs.begin(stage_s, g31 + my_ofs - flushed_bits, 0u);
         // The 16 pixels are emitted as 2 halves of 8 by a ROLLED loop (a fully unrolled body is ~80 KB of SASS and stalls
@@ -454,6 +470,11 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
             const uint32_t r = run_before16<M>(eqm, r_in, nvp);
             if (r) put_match16(bs, match_s, r);
         }
+        // row bits after this step (the next step's first offset was loaded a whole emission ago)
+        const uint32_t step_end = more ? __shfl_sync(kFullMask, mine.x, 0) : row_total;
+        const uint32_t fill = g31 + step_end - flushed_bits;            // live bits in the staging buffer after this step
+        const uint32_t nwords = fill >> 5;
+        if (lane == 0) stage[nwords] = 0u;                               // the one word no lane completes in this step
         __syncwarp();                                                    // all complete words are stored ...
         bs.end();                                                        // ... before the partial ones are OR-ed in
         __syncwarp();
@@ -469,8 +490,12 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         if (nwords) first_pending = false;
         gptr += nwords;
         flushed_bits += nwords << 5;
+        if (more) step++;
+        else {                                                           // end of the scanline: its last, partial word
+            if (lane == 0 && leftover) atomicOr(gptr, leftover);
+            step = 0; r_i++;
+        }
     }
-    if (lane == 0 && leftover) atomicOr(gptr, leftover);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -506,7 +531,8 @@ void launch_hist16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t
 
 void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
-    dim3 grid((p.h + kPack16Rows - 1) / kPack16Rows, n);
+    constexpr uint32_t rows_per_cta = kPack16Rows * kPack16RowsPerWarp;
+    dim3 grid((p.h + rows_per_cta - 1) / rows_per_cta, n);
     if (chans == 4) { FPNGB_SET_SMEM(pack_rows16_kernel<4>, pack16_smem<4>()); pack_rows16_kernel<4><<<grid, 32 * kPack16Rows, pack16_smem<4>(), s>>>(p); }
     else { FPNGB_SET_SMEM(pack_rows16_kernel<3>, pack16_smem<3>()); pack_rows16_kernel<3><<<grid, 32 * kPack16Rows, pack16_smem<3>(), s>>>(p); }
 }

@@ -23,10 +23,7 @@ constexpr int kStep16 = 32 * kPix16;             // pixels per warp step
 // contiguous bytes each) into the warp's shared-memory tile and arms the warp's mbarrier with the byte count; all lanes
 // wait on the mbarrier phase, read their own 16 pixels (48 / 64 contiguous bytes per lane) into registers, and the next
 // step's copies are issued while this step is processed.  SASS: UBLKCP + SYNCS.
-constexpr int kTileBytes = 2048;                        // one scanline step: 512 pixels x (3|4) bytes <= 2048
-constexpr int kTileStageBytes = 2 * kTileBytes;         // cur + prev
 constexpr int kTileLaneBytes = 80;                      // padded per-lane slot of the cp.async (RGBA) variant
-constexpr int kTileWarpBytes = 2 * 32 * kTileLaneBytes + 16;   // max over both variants: 2 x 2560 (padded cur+prev) / 4096 + mbarrier
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,8 +58,9 @@ template <int CHANS>
 struct Walk16Tma {
     static constexpr int kWords = 4 * CHANS;     // filtered words per lane per step (16 pixels)
     static constexpr uint32_t kStepBytes = kStep16 * CHANS;
-    static constexpr uint32_t kMbarOfs = kTileStageBytes;     // the warp's mbarrier sits behind the two 2 KiB tiles
-    static constexpr int kWarpBytes = kTileStageBytes + 16;   // shared memory per warp
+    static constexpr uint32_t kTile = kStepBytes;             // one scanline step: 1536 (RGB) / 2048 (RGBA) bytes
+    static constexpr uint32_t kMbarOfs = 2 * kTile;           // the warp's mbarrier sits behind the cur and prev tiles
+    static constexpr int kWarpBytes = 2 * kTile + 16;         // shared memory per warp
 
     __device__ __forceinline__ void init(uint32_t lane, uint8_t* warp_tiles)
     {
@@ -82,19 +80,20 @@ struct Walk16Tma {
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             mbar_expect_tx(mbar, prev ? 2u * bytes : bytes);
             tma_bulk_g2s(warp_tiles, cur + b, bytes, mbar);
-            if (prev) tma_bulk_g2s(warp_tiles + kTileBytes, prev + b, bytes, mbar);
+            if (prev) tma_bulk_g2s(warp_tiles + kTile, prev + b, bytes, mbar);
         }
     }
 
     // wait for the step to land, read the lane's 16 pixels, apply the Up filter (fpng.cpp:1605-1652), optionally add the
     // Adler partials (sum of bytes, position-weighted sum) of these 16*CHANS bytes
+    // `phase` counts the prefetches consumed so far by this warp (mbarrier parity); `step` is the position inside the row
     template <bool kAdler>
-    __device__ __forceinline__ void consume(bool have_prev, uint32_t step, uint32_t bpl, uint32_t lane, uint8_t* warp_tiles,
+    __device__ __forceinline__ void consume(bool have_prev, uint32_t phase, uint32_t step, uint32_t bpl, uint32_t lane, uint8_t* warp_tiles,
                                             uint32_t (&dw)[kWords], uint32_t& sumA, unsigned long long& sumB) const
     {
-        mbar_wait(warp_tiles + kMbarOfs, step & 1u);
+        mbar_wait(warp_tiles + kMbarOfs, phase & 1u);
         const uint8_t* tc = warp_tiles + lane * (16 * CHANS);
-        const uint8_t* tp = tc + kTileBytes;
+        const uint8_t* tp = tc + kTile;
         const uint32_t lane_base = step * kStepBytes + lane * (16u * CHANS);     // byte offset of the lane's first byte in the row
 #pragma unroll
         for (int i = 0; i < CHANS; i++) {
@@ -177,7 +176,7 @@ struct Walk16Padded {
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
     template <bool kAdler>
-    __device__ __forceinline__ void consume(bool have_prev, uint32_t step, uint32_t, uint32_t lane, uint8_t* warp_tiles,
+    __device__ __forceinline__ void consume(bool have_prev, uint32_t, uint32_t step, uint32_t, uint32_t lane, uint8_t* warp_tiles,
                                             uint32_t (&dw)[kWords], uint32_t& sumA, unsigned long long& sumB) const
     {
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
