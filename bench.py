@@ -245,7 +245,7 @@ def run_reference(args, wl):
         "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -480,13 +480,33 @@ def run_ours(args, wl):
             dv, dcores, dsample, dkind = cpu_reference_decode_run(wl, args.kind, max(2.0, args.cpu_seconds / 3))
             line["decode"]["cpu_baseline"] = {"value": float(dv), "unit": "MP/s", "cores": dcores, "kind": dkind, "sample": dsample}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL with NCCL_DEBUG=VERSION, torchrun banners) also write to
+    fd 1, so keep a private copy of the real stdout for the JSON line and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
