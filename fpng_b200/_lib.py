@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
     L.fpngb_host_free.restype = None
     L.fpngb_host_free.argtypes = [C.c_void_p]
     L.fpngb_launch_count.restype = C.c_uint64
+    L.fpngb_debug_rows_per_warp.restype = None
+    L.fpngb_debug_rows_per_warp.argtypes = [C.c_uint32]
     L.fpngb_debug_static_table.restype = C.c_int
     L.fpngb_debug_static_table.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, u32p]
     _lib = L

@@ -8,8 +8,16 @@ namespace fpngb {
 
 constexpr int kScan16Rows = 8;                   // warps (scanlines) per CTA, scan
 constexpr int kPack16Rows = 4;                   // warps per CTA, pack (larger staging buffers)
-constexpr int kPack16RowsPerWarp = 5;            // consecutive scanlines per warp, pack: amortises the CTA prologue and lets the first tile of
-                                                 // a scanline be prefetched during the previous scanline's last step
+constexpr uint32_t kRowsPerWarp16 = 5;           // consecutive scanlines per warp (pack kernel) on large batches: amortises the CTA prologue and
+                                                 // lets a scanline's first tile be prefetched during the previous scanline's last step
+// small jobs (a single image) keep one scanline per warp so that the grid still fills the GPU
+static uint32_t g_rows_per_warp_override = 0;    // tests force both shapes of the kernels on small inputs (fpngb_debug_rows_per_warp)
+void set_rows_per_warp16(uint32_t v) { g_rows_per_warp_override = v > 64u ? 64u : v; }
+static uint32_t rows_per_warp16(uint32_t n, uint32_t h)
+{
+    if (g_rows_per_warp_override) return g_rows_per_warp_override;
+    return (size_t)n * h >= 148u * 64u * kRowsPerWarp16 ? kRowsPerWarp16 : 1u;
+}
 // staging words per warp step: lead-in (31) + filter literal (12) + 512 pixel slots of [pending match 18 bits][literal 12*CHANS bits]
 template <int CHANS> __host__ __device__ constexpr int stage16_words() { return ((31 + 12 + 512 * (18 + 12 * CHANS)) / 32 + 1 + 15) / 16 * 16; }
 
@@ -304,7 +312,7 @@ __device__ __forceinline__ void put_event16(BitStager16& bs, uint32_t s_match_sa
 }
 
 template <int CHANS>
-__global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParams p)
+__global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParams p, uint32_t rows_per_warp)
 {
     constexpr uint32_t M = max_match_pixels(CHANS);
     constexpr int kHalfWords = 2 * CHANS;        // filtered words of 8 pixels
@@ -315,12 +323,12 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t img = blockIdx.y;
-    const uint32_t row0 = (blockIdx.x * kPack16Rows + warp) * kPack16RowsPerWarp;      // this warp's first scanline
+    const uint32_t row0 = (blockIdx.x * kPack16Rows + warp) * rows_per_warp;           // this warp's first scanline
     const CodeBook* book = p.books + (size_t)img * p.book_stride;
     const ImageState st = p.st[img];
     if (st.stored) {                             // stored-block fallback (fpng.cpp:818-866): strided copy of the rows
         const uint32_t bpl_s = p.w * CHANS;
-        for (uint32_t y = row0; y < min(row0 + kPack16RowsPerWarp, p.h); y++)
+        for (uint32_t y = row0; y < min(row0 + rows_per_warp, p.h); y++)
             store_row_raw(p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl_s, p.out + (size_t)img * p.out_stride + kPngHeaderSize,
                           y, bpl_s, lane, &p.row_adler[(size_t)img * p.h + y]);
         return;
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     if (row0 >= p.h) return;
 
     const uint32_t w = p.w, bpl = w * CHANS;
-    const uint32_t nrows = min((uint32_t)kPack16RowsPerWarp, p.h - row0);
+    const uint32_t nrows = min(rows_per_warp, p.h - row0);
     const uint8_t* img_px = p.pixels + (size_t)img * p.image_stride;
     uint32_t* stage = s_stage_all + warp * stage16_words<CHANS>();
     const uint32_t stage_s = smem_u32(stage), lit_s = smem_u32(s_lit), match_s = smem_u32(s_match);
@@ -516,6 +524,7 @@ template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk1
 
 void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
+    // one scanline per warp: the multi-scanline sequence that pays off in the pack kernel measured neutral (RGB) to 4 % slower (RGBA) here
     dim3 grid((p.h + kScan16Rows - 1) / kScan16Rows, n);
     if (chans == 4) { FPNGB_SET_SMEM(row_scan16_kernel<4>, scan16_smem<4>()); row_scan16_kernel<4><<<grid, 32 * kScan16Rows, scan16_smem<4>(), s>>>(p); }
     else { FPNGB_SET_SMEM(row_scan16_kernel<3>, scan16_smem<3>()); row_scan16_kernel<3><<<grid, 32 * kScan16Rows, scan16_smem<3>(), s>>>(p); }
@@ -531,10 +540,10 @@ void launch_hist16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t
 
 void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
-    constexpr uint32_t rows_per_cta = kPack16Rows * kPack16RowsPerWarp;
+    const uint32_t rpw = rows_per_warp16(n, p.h), rows_per_cta = kPack16Rows * rpw;
     dim3 grid((p.h + rows_per_cta - 1) / rows_per_cta, n);
-    if (chans == 4) { FPNGB_SET_SMEM(pack_rows16_kernel<4>, pack16_smem<4>()); pack_rows16_kernel<4><<<grid, 32 * kPack16Rows, pack16_smem<4>(), s>>>(p); }
-    else { FPNGB_SET_SMEM(pack_rows16_kernel<3>, pack16_smem<3>()); pack_rows16_kernel<3><<<grid, 32 * kPack16Rows, pack16_smem<3>(), s>>>(p); }
+    if (chans == 4) { FPNGB_SET_SMEM(pack_rows16_kernel<4>, pack16_smem<4>()); pack_rows16_kernel<4><<<grid, 32 * kPack16Rows, pack16_smem<4>(), s>>>(p, rpw); }
+    else { FPNGB_SET_SMEM(pack_rows16_kernel<3>, pack16_smem<3>()); pack_rows16_kernel<3><<<grid, 32 * kPack16Rows, pack16_smem<3>(), s>>>(p, rpw); }
 }
 
 }  // namespace fpngb

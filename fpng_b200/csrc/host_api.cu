@@ -329,6 +329,9 @@ uint64_t fpngb_launch_count(void) { return g_launches.load(); }
 
 size_t fpngb_max_encoded_size(uint32_t w, uint32_t h, uint32_t chans) { return max_encoded_size(w, h, chans); }
 
+// test hook: scanlines per warp of the 16-pixel scan/pack kernels (0 = automatic); not part of the reference surface
+FPNGB_API void fpngb_debug_rows_per_warp(uint32_t v) { set_rows_per_warp16(v); }
+
 // exposes the static code books to the tests (sizes[288], codes[288]); not part of the reference surface
 FPNGB_API int fpngb_debug_static_table(uint32_t chans, uint8_t* sizes, uint16_t* codes, uint32_t* hdr_bits)
 {

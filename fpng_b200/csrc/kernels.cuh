@@ -69,6 +69,7 @@ bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t
 void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s);
 void launch_hist16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s);
 void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s);
+void set_rows_per_warp16(uint32_t v);          // 0 = automatic (5 scanlines per warp on large batches, 1 otherwise)
 void launch_offsets(const OffsetsParams& p, uint32_t n, cudaStream_t s);
 void launch_pack(const PackParams& p, uint32_t n, uint32_t chans, int mode, cudaStream_t s);
 void launch_adler_finalize(const AdlerParams& p, uint32_t n, cudaStream_t s);

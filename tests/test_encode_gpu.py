@@ -17,16 +17,27 @@ SHAPES = [(1, 1), (1, 9), (2, 2), (5, 3), (15, 2), (16, 2), (20, 1), (24, 1), (6
           (528, 3), (1024, 5), (1040, 2), (1920, 3), (4096, 2), (8192, 1)]   # multi-step rows on the 16-pixel-per-lane kernels
 
 
+@pytest.fixture
+def rows_per_warp(request):
+    """Forces the scanlines-per-warp shape of the 16-pixel scan/pack kernels (large batches use 5, small ones 1; 0 = automatic)
+    so that small test images exercise the pipelined multi-scanline sequence too."""
+    from fpng_b200 import _lib
+    _lib.lib().fpngb_debug_rows_per_warp(request.param)
+    yield request.param
+    _lib.lib().fpngb_debug_rows_per_warp(0)
+
+
+@pytest.mark.parametrize("rows_per_warp", [5, 1, 3], indirect=True)
 @pytest.mark.parametrize("kind", ["g0", "g1", "g2", "runs", "mut", "zero"])
 @pytest.mark.parametrize("chans", [3, 4])
-def test_encode_byte_exact_vs_oracle(gpu, oracle, kind, chans):
-    for i, (w, h) in enumerate(SHAPES):
+def test_encode_byte_exact_vs_oracle(gpu, oracle, kind, chans, rows_per_warp):
+    for i, (w, h) in enumerate(SHAPES + [(512, 23), (1040, 11)]):
         img = imagegen.make(kind, w, h, chans, 100 + i)
         for flags in (0, gpu.FPNG_ENCODE_SLOWER, gpu.FPNG_FORCE_UNCOMPRESSED):
             ok, png = gpu.fpng_encode_image_to_memory(img, w, h, chans, flags)
             assert ok
             exp = oracle.encode(img, w, h, chans, flags)
-            assert png == exp, (kind, w, h, chans, flags, len(png), len(exp))
+            assert png == exp, (kind, w, h, chans, flags, rows_per_warp, len(png), len(exp))
 
 
 def test_encode_matches_golden_vectors(gpu):
