@@ -53,3 +53,18 @@ def test_get_info_on_corrupted_containers_matches_reference(oracle, ref):
                 assert got[1:] == tuple(exp[1:4]), (got, exp)
             n += 1
     assert n > 1000
+
+
+def test_product_static_code_books_match_oracle(oracle):
+    """The 1-pass code books the product derives at init by parsing the two pre-serialised block headers
+    (csrc/static_tables.h; reference: fpng.cpp:184-371 g_dyn_huff_3/4 + their size/code tables) -- host code, no GPU."""
+    import ctypes as C
+    from fpng_b200 import _lib
+    L = _lib.lib()
+    for chans in (3, 4):
+        sizes = np.zeros(288, np.uint8); codes = np.zeros(288, np.uint16); hb = C.c_uint32(0)
+        rc = L.fpngb_debug_static_table(chans, sizes.ctypes.data_as(C.c_void_p), codes.ctypes.data_as(C.c_void_p), C.byref(hb))
+        assert rc == 0
+        esz, ecd, ehb = oracle.static_table(chans)
+        assert np.array_equal(sizes, esz) and hb.value == ehb
+        assert np.array_equal(codes[:257], ecd[:257])          # literal codes + end of block (the hook reports no length codes)
