@@ -293,12 +293,16 @@ __global__ void __launch_bounds__(1024) compact_offsets_kernel(const uint32_t* _
 }
 
 __global__ void __launch_bounds__(256) compact_copy_kernel(const uint8_t* __restrict__ files, size_t stride, const uint32_t* __restrict__ sizes,
-                                                            const unsigned long long* __restrict__ offsets, uint8_t* __restrict__ dst, size_t dst_cap)
+                                                            unsigned long long* __restrict__ offsets, uint32_t n, uint8_t* __restrict__ dst, size_t dst_cap)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t nvec = (sizes[f] + 15u) / 16u;
     const unsigned long long o = offsets[f];
-    if (o + (unsigned long long)nvec * 16ull > dst_cap) return;
+    if (o + (unsigned long long)nvec * 16ull > dst_cap) {
+        // the file does not fit: it is NOT copied, and bit 63 of offsets[n] (the total) tells the caller so
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&offsets[n], 1ull << 63);
+        return;
+    }
     const uint4* src = reinterpret_cast<const uint4*>(files + (size_t)f * stride);
     uint4* d = reinterpret_cast<uint4*>(dst + o);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) d[i] = src[i];
@@ -309,7 +313,7 @@ void launch_compact(const uint8_t* files, size_t stride, const uint32_t* sizes, 
 {
     compact_offsets_kernel<<<1, 1024, 0, s>>>(sizes, n, offsets);
     dim3 grid(64, n);
-    compact_copy_kernel<<<grid, 256, 0, s>>>(files, stride, sizes, offsets, dst, dst_cap);
+    compact_copy_kernel<<<grid, 256, 0, s>>>(files, stride, sizes, offsets, n, dst, dst_cap);
 }
 
 }  // namespace fpngb

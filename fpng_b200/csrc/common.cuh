@@ -27,7 +27,9 @@ struct CodeBook {
     uint8_t  match_bits[88];  // total_bits per match length in pixels
     uint8_t  hdr[kMaxHdrBytes];
     uint8_t  sym_size[288];   // raw lit/len code sizes (used to build the decoder tables / tests)
-    uint8_t  pad_[8];
+    uint8_t  lit1_rule;       // RGBA 1-pass only: a one-pixel match can cost more than four literals under this table, so the
+                              //   reference's check at fpng.cpp:1520-1528 is live (never with the shipped table)
+    uint8_t  pad_[7];
 };
 
 // Per-image state produced by the offsets kernel and consumed by pack / checksum kernels.

@@ -114,6 +114,8 @@ int fpngb_decode_batch_device(const void* d_files, size_t file_stride, const uin
     if (!c.ready) return FPNGB_ERR_NOT_INITIALIZED;
     if (!d_files || !file_sizes || !idat_ofs || !idat_len || !d_out || !d_status || n == 0 || n > 65535) return FPNGB_ERR_INVALID_ARG;
     if ((chans_in_file != 3 && chans_in_file != 4) || (desired_chans != 3 && desired_chans != 4) || !w || !h) return FPNGB_ERR_INVALID_ARG;
+    // the container limits of fpng_get_info (fpng.cpp:2966-2971): keeps w * chans and the scratch pitch inside 32 bits
+    if (w > (1u << 24) || h > (1u << 24) || (uint64_t)w * h > (1ull << 30)) return FPNGB_ERR_INVALID_ARG;
     if ((uint64_t)w * h * desired_chans > 0xFFFFFFFFull || out_stride < (size_t)w * h * desired_chans) return FPNGB_ERR_BUFFER_TOO_SMALL;
     if (file_stride % 4 || (uintptr_t)d_files % 4) return FPNGB_ERR_ALIGNMENT;
     std::vector<FileDesc> fds(n);
@@ -199,13 +201,15 @@ int fpngb_decode_batch_host(const void* const* files, const uint32_t* sizes, uin
     constexpr int kSlots = 3;
     const size_t fstride = align_up((size_t)max_size + 16, 16), pstride = align_up((size_t)need, 16);
     uint32_t per_chunk = (uint32_t)(((size_t)64 << 20) / need); if (per_chunk < 1) per_chunk = 1; if (per_chunk > n) per_chunk = n;
+    if (per_chunk > 65535u) per_chunk = 65535u;                     // grid.y limit of the batch kernels (tiny images)
     const size_t slot_in = per_chunk * fstride, slot_out = per_chunk * pstride + align_up(per_chunk * 4, 256);
     int rc = c.dev_in.reserve(kSlots * slot_in); if (rc) return rc;
     rc = c.dev_out.reserve(kSlots * slot_out); if (rc) return rc;
     rc = c.pin_small.reserve(kSlots * align_up(per_chunk * 4, 256)); if (rc) return rc;
     if (!c.copy_in) { FPNGB_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking)); FPNGB_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking)); }
-    cudaEvent_t ev_in[kSlots], ev_done[kSlots], ev_out[kSlots];
-    for (int i = 0; i < kSlots; i++) { cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming); }
+    EventSet<3 * kSlots> evs;                                       // destroyed on every exit path
+    if (!evs.ok) return FPNGB_ERR_INTERNAL;
+    cudaEvent_t* ev_in = evs.ev; cudaEvent_t* ev_done = evs.ev + kSlots; cudaEvent_t* ev_out = evs.ev + 2 * kSlots;
     // decodable files, in order
     std::vector<uint32_t> idx; idx.reserve(n);
     for (uint32_t i = 0; i < n; i++) if (!status[i]) idx.push_back(i);
@@ -250,7 +254,6 @@ int fpngb_decode_batch_host(const void* const* files, const uint32_t* sizes, uin
         }
         if (cudaGetLastError() != cudaSuccess) result = FPNGB_ERR_INTERNAL;
     }
-    for (int i = 0; i < kSlots; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_out[i]); }
     return result;
 }
 

@@ -79,12 +79,19 @@ __global__ void __launch_bounds__(kScanThreads) row_scan_kernel(ScanParams p)
                 }
                 if (t.tail) { uint32_t s, xb, xv; deflate_len_code(t.tail * CHANS, s, xb, xv); atomicAdd(&s_hist[s], 1u); }
             } else {
+                // RGBA 1-pass "one-pixel match vs four literals" (fpng.cpp:1520-1528): a match token of exactly one pixel costs
+                // min(match, literals) -- strictly: literals are taken iff match bits > literal bits.  Only compiled into the
+                // rule-aware instantiation; p.lit1_rule is warp-uniform.
+                uint32_t tail_cost = s_match[t.tail];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    bits += s_match[t.mlen[k]];
+                    uint32_t mc = s_match[t.mlen[k]];
+                    if (CHANS == 4 && p.lit1_rule && t.mlen[k] == 1u) { const uint32_t lb = literal_bits<CHANS>(s_lit, run_pixel_before(t, k)); if (mc > lb) mc = lb; }
+                    bits += mc;
                     if (t.litmask & (1u << k)) bits += literal_bits<CHANS>(s_lit, t.px[k]);
                 }
-                bits += s_match[t.tail];
+                if (CHANS == 4 && p.lit1_rule && t.tail == 1u) { const uint32_t lb = literal_bits<CHANS>(s_lit, run_pixel_before(t, t.nvp)); if (tail_cost > lb) tail_cost = lb; }
+                bits += tail_cost;
 
                 // Adler-32 partials over the filtered bytes (fpng.cpp:403-487 computes the same sum serially)
                 uint32_t t1 = 0, t2 = 0;
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(kScanThreads) row_scan_kernel(ScanParams p)
                 if (t.nvp > 0 && p0 + t.nvp == w && y == p.h - 1) {
                     const uint32_t k = t.nvp - 1;
                     uint32_t lu;
-                    if (t.tail) lu = s_match[t.tail];
+                    if (t.tail) lu = tail_cost;
                     else if (!(t.litmask & (1u << k))) lu = s_match[t.mlen[k]];
                     else lu = literal_bits<CHANS>(s_lit, t.px[k]) + ((w == 1 && p.merge_first_unit) ? s_lit[filt] : 0u);
                     p.st[img].last_unit_bits = lu;
@@ -338,12 +345,21 @@ __global__ void __launch_bounds__(kPackThreads) pack_rows_kernel(PackParams p)
         classify_step<CHANS>(t, p0, w, carry, lane);
 
         uint32_t nb = (step == 0 && lane == 0) ? (fcode >> 16) : 0u;
+        // bit j < 4: the one-pixel match flushed at slot j is written as four literals; bit 4: same for the row-end token
+        // (RGBA 1-pass rule, fpng.cpp:1520-1528; p.lit1_rule is warp-uniform and zero for every other mode)
+        uint32_t as_lits = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            nb += s_match[t.mlen[k]] >> 24;
+            uint32_t mc = s_match[t.mlen[k]] >> 24;
+            if (CHANS == 4 && p.lit1_rule && t.mlen[k] == 1u) { const uint32_t lb = literal_bits_w<CHANS>(s_lit, run_pixel_before(t, k)); if (mc > lb) { mc = lb; as_lits |= 1u << k; } }
+            nb += mc;
             if (t.litmask & (1u << k)) nb += literal_bits_w<CHANS>(s_lit, t.px[k]);
         }
-        nb += s_match[t.tail] >> 24;
+        {
+            uint32_t mc = s_match[t.tail] >> 24;
+            if (CHANS == 4 && p.lit1_rule && t.tail == 1u) { const uint32_t lb = literal_bits_w<CHANS>(s_lit, run_pixel_before(t, t.nvp)); if (mc > lb) { mc = lb; as_lits |= 16u; } }
+            nb += mc;
+        }
 
         uint32_t step_bits;
         const uint32_t ofs = warp_excl_scan_u32(nb, lane, step_bits);
@@ -353,10 +369,12 @@ __global__ void __launch_bounds__(kPackThreads) pack_rows_kernel(PackParams p)
         if (step == 0 && lane == 0) bs.put(fcode & 0xFFFFu, fcode >> 16);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (t.mlen[k]) { const uint32_t m = s_match[t.mlen[k]]; bs.put(m & 0xFFFFFFu, m >> 24); }
+            if (as_lits & (1u << k)) put_literal<CHANS>(bs, s_lit, run_pixel_before(t, k));
+            else if (t.mlen[k]) { const uint32_t m = s_match[t.mlen[k]]; bs.put(m & 0xFFFFFFu, m >> 24); }
             if (t.litmask & (1u << k)) put_literal<CHANS>(bs, s_lit, t.px[k]);
         }
-        if (t.tail) { const uint32_t m = s_match[t.tail]; bs.put(m & 0xFFFFFFu, m >> 24); }
+        if (as_lits & 16u) put_literal<CHANS>(bs, s_lit, run_pixel_before(t, t.nvp));
+        else if (t.tail) { const uint32_t m = s_match[t.tail]; bs.put(m & 0xFFFFFFu, m >> 24); }
         bs.end();
         __syncwarp();
 

@@ -14,6 +14,7 @@
 #include <atomic>
 #include <mutex>
 #include <new>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -112,6 +113,14 @@ static bool build_static_book(CodeBook& cb, const uint8_t* hdr, uint32_t nbytes,
     if (br.get(1) != 1 || br.get(2) != 2) return false;
     uint8_t lit_sizes[288], dist_sizes[32];
     if (!read_code_sizes(br, lit_sizes, dist_sizes) || br.pos != cb.hdr_bits) return false;
+    // fpng decoders (fpng.cpp:2007, 2058-2074) accept literal/length code sizes up to 12 only, and the pack kernels
+    // hard-code the distance code as the single bit 0: exactly the table the trainer emits (fpng.cpp:1096-1098) --
+    // 1-bit codes at distance symbols chans-1 (code 0) and optionally chans (code 1), nothing else.
+    for (int v = 0; v < 288; v++) if (lit_sizes[v] > 12) return false;
+    for (uint32_t d = 0; d < 32; d++) {
+        const bool allowed = d == chans - 1 || d == chans;
+        if (dist_sizes[d] != 0 && !(allowed && dist_sizes[d] == 1)) return false;
+    }
     if (dist_sizes[chans - 1] != 1) return false;
     uint16_t codes[288];
     canonical_codes(lit_sizes, 288, codes);
@@ -119,6 +128,10 @@ static bool build_static_book(CodeBook& cb, const uint8_t* hdr, uint32_t nbytes,
     for (uint32_t n = 1; n <= M; n++) { uint32_t s, xb, xv; deflate_len_code(n * chans, s, xb, xv); if (!lit_sizes[s]) return false; }
     for (int v = 0; v <= 256; v++) if (!lit_sizes[v]) return false;
     finish_codebook(cb, lit_sizes, codes, chans);
+    // can "size(len sym 258) + 1 > sum of four literal sizes" (fpng.cpp:1520-1528) ever hold under this table?
+    uint32_t min_lit = 255;
+    for (int v = 0; v < 256; v++) min_lit = lit_sizes[v] < min_lit ? lit_sizes[v] : min_lit;
+    cb.lit1_rule = (chans == 4 && cb.match_bits[1] > 4u * min_lit) ? 1 : 0;
     return true;
 }
 
@@ -238,7 +251,10 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     // second-generation kernels (16 pixels per lane, coalesced 128-bit loads) whenever every scanline is 16-byte aligned;
     // FPNGB_FORCE_GENERIC=1 keeps the generic kernels (tests compare both)
     static const bool force_generic = getenv("FPNGB_FORCE_GENERIC") && atoi(getenv("FPNGB_FORCE_GENERIC")) != 0;
-    const bool v2 = !force_generic && walk16_eligible(d_pixels, image_stride, w, chans);
+    // RGBA 1-pass under a table where a one-pixel match can lose against four literals: only the generic kernels
+    // implement the reference's check (fpng.cpp:1520-1528); it cannot fire with the shipped table
+    const uint32_t lit1_rule = (!two_pass && chans == 4 && c.h_static_books[1].lit1_rule) ? 1u : 0u;
+    const bool v2 = !force_generic && !lit1_rule && walk16_eligible(d_pixels, image_stride, w, chans);
     const CodeBook* books = two_pass ? ws.books : c.d_static_books + (chans == 4 ? 1 : 0);
     const uint32_t book_stride = two_pass ? 1u : 0u;
 
@@ -248,6 +264,7 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     sp.row_bits = ws.row_bits; sp.row_adler = ws.row_adler; sp.st = ws.st; sp.hist = ws.hist;
     sp.merge_first_unit = (!two_pass && chans == 3) ? 1u : 0u;
     sp.lane_ofs = ws.lane_ofs; sp.lane_ofs_pitch = ws.lane_ofs_pitch;
+    sp.lit1_rule = lit1_rule;
 
     ProfSet* ps = prof_begin(s);
     if (two_pass) {
@@ -272,6 +289,7 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     PackParams pp{};
     pp.pixels = d_pixels; pp.image_stride = image_stride; pp.w = w; pp.h = h; pp.books = books; pp.book_stride = book_stride;
     pp.row_ofs = ws.row_ofs; pp.row_bits = ws.row_bits; pp.lane_ofs = ws.lane_ofs; pp.lane_ofs_pitch = ws.lane_ofs_pitch; pp.row_adler = ws.row_adler; pp.st = ws.st; pp.out = d_out; pp.out_stride = out_stride;
+    pp.lit1_rule = lit1_rule;
     if (v2) launch_pack16(pp, n, chans, s); else launch_pack(pp, n, chans, mode, s);
     prof_mark(ps, kProfPack, s);
 
@@ -409,16 +427,15 @@ int fpngb_encode_batch_host(const void* pixels, size_t image_stride, uint32_t n,
     constexpr int kSlots = 3;
     const size_t target = (size_t)64 << 20;                         // ~64 MiB of pixels per chunk
     uint32_t per_chunk = (uint32_t)(target / in_bytes); if (per_chunk < 1) per_chunk = 1; if (per_chunk > n) per_chunk = n;
+    if (per_chunk > 65535u) per_chunk = 65535u;                     // grid.y limit of the batch kernels (tiny images)
     const size_t slot_in = align_up(per_chunk * in_bytes, 256), slot_out = per_chunk * dstride, slot_sz = align_up(per_chunk * 4, 256);
     int rc = c.dev_in.reserve(kSlots * slot_in); if (rc) return rc;
     rc = c.dev_out.reserve(kSlots * (slot_out + slot_sz)); if (rc) return rc;
     rc = c.pin_small.reserve(kSlots * slot_sz); if (rc) return rc;
     if (!c.copy_in) { FPNGB_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking)); FPNGB_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking)); }
-    cudaEvent_t ev_in[kSlots], ev_done[kSlots], ev_sizes[kSlots], ev_out[kSlots];
-    for (int i = 0; i < kSlots; i++) {
-        FPNGB_CUDA_OK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming)); FPNGB_CUDA_OK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
-        FPNGB_CUDA_OK(cudaEventCreateWithFlags(&ev_sizes[i], cudaEventDisableTiming)); FPNGB_CUDA_OK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-    }
+    EventSet<4 * kSlots> evs;                                       // destroyed on every exit path
+    if (!evs.ok) return FPNGB_ERR_INTERNAL;
+    cudaEvent_t* ev_in = evs.ev; cudaEvent_t* ev_done = evs.ev + kSlots; cudaEvent_t* ev_sizes = evs.ev + 2 * kSlots; cudaEvent_t* ev_out = evs.ev + 3 * kSlots;
     const uint32_t nchunks = (n + per_chunk - 1) / per_chunk;
     const bool contiguous = image_stride == in_bytes;
     int result = FPNGB_OK;
@@ -462,7 +479,6 @@ int fpngb_encode_batch_host(const void* pixels, size_t image_stride, uint32_t n,
     }
     if (result == FPNGB_OK) result = finish(nchunks - 1);
     cudaStreamSynchronize(c.copy_in); cudaStreamSynchronize(c.stream); cudaStreamSynchronize(c.copy_out);
-    for (int i = 0; i < kSlots; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_sizes[i]); cudaEventDestroy(ev_out[i]); }
     if (result == FPNGB_OK) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) result = 1000 + (int)e; }
     return result;
 }
@@ -499,58 +515,85 @@ FPNGB_API int fpngb_profile_read(float* ms, int nslots)
 }
 
 // fpng_crc32 / fpng_adler32 utilities (src/fpng.h:26-31) on host buffers.  Buffers of at least 4 KiB go through the
-// device kernels; shorter ones (chunk headers, IHDR) use the host table that the container code needs anyway.
-uint32_t fpngb_crc32(const void* data, size_t size, uint32_t prev)
+// device kernels; shorter ones (chunk headers, IHDR) and calls made before fpngb_init() use the host table that the
+// container code needs anyway (documented in include/fpng_b200.h).  The *_ex forms report device errors; the plain forms
+// keep the reference's signatures and, because 0 is a valid checksum, report a device failure on stderr before returning 0.
+int fpngb_crc32_ex(const void* data, size_t size, uint32_t prev, uint32_t* out)
 {
-    if (!data || !size) return prev;
-    if (!g_ctx.ready || size < 4096 || size > 0xFFFFFF00ull) return host_crc32(data, size, prev);
+    if (!out) return FPNGB_ERR_INVALID_ARG;
+    *out = prev;
+    if (!data || !size) return FPNGB_OK;
+    if (!g_ctx.ready || size < 4096 || size > 0xFFFFFF00ull) { *out = host_crc32(data, size, prev); return FPNGB_OK; }
     Context& c = g_ctx;
     std::lock_guard<std::mutex> lk(c.mu);
-    if (cudaSetDevice(c.device) != cudaSuccess) return 0;
+    FPNGB_CUDA_OK(cudaSetDevice(c.device));
     const size_t padded = align_up(size + 16, 16);
-    if (c.dev_in.reserve(padded + 256)) return 0;
+    int rc = c.dev_in.reserve(padded + 256); if (rc) return rc;
     ImageState hst{}; hst.zsize = (uint32_t)size - kPngHeaderSize;       // kernel computes L = 58 + zsize = size
     ImageState* dst = (ImageState*)((uint8_t*)c.dev_in.p + padded);
-    cudaMemcpyAsync(c.dev_in.p, data, size, cudaMemcpyHostToDevice, c.stream);
-    cudaMemcpyAsync(dst, &hst, sizeof hst, cudaMemcpyHostToDevice, c.stream);
+    FPNGB_CUDA_OK(cudaMemcpyAsync(c.dev_in.p, data, size, cudaMemcpyHostToDevice, c.stream));
+    FPNGB_CUDA_OK(cudaMemcpyAsync(dst, &hst, sizeof hst, cudaMemcpyHostToDevice, c.stream));
     CrcParams cp{};
     cp.out = (uint8_t*)c.dev_in.p; cp.out_stride = 0; cp.st = dst; cp.max_tiles = crc_ctas_for(size); cp.msg_start = 0; cp.init_xor = ~prev;
     launch_crc(cp, 1, c.stream);
     count_launch(1);
+    FPNGB_CUDA_OK(cudaGetLastError());
     uint8_t be[4] = {0, 0, 0, 0};
-    cudaMemcpyAsync(be, (uint8_t*)c.dev_in.p + size, 4, cudaMemcpyDeviceToHost, c.stream);
-    if (cudaStreamSynchronize(c.stream) != cudaSuccess) return 0;
-    return ((uint32_t)be[0] << 24) | ((uint32_t)be[1] << 16) | ((uint32_t)be[2] << 8) | be[3];
+    FPNGB_CUDA_OK(cudaMemcpyAsync(be, (uint8_t*)c.dev_in.p + size, 4, cudaMemcpyDeviceToHost, c.stream));
+    FPNGB_CUDA_OK(cudaStreamSynchronize(c.stream));
+    *out = ((uint32_t)be[0] << 24) | ((uint32_t)be[1] << 16) | ((uint32_t)be[2] << 8) | be[3];
+    return FPNGB_OK;
 }
 
-uint32_t fpngb_adler32(const void* data, size_t size, uint32_t adler)
+int fpngb_adler32_ex(const void* data, size_t size, uint32_t adler, uint32_t* out)
 {
+    if (!out) return FPNGB_ERR_INVALID_ARG;
+    *out = adler;
     uint32_t a = adler & 0xFFFF, b = adler >> 16;
-    if (!data || !size) return adler;
+    if (!data || !size) return FPNGB_OK;
     if (!g_ctx.ready || size < 4096) {
         const uint8_t* p = (const uint8_t*)data;
         for (size_t i = 0; i < size; i++) { a = (a + p[i]) % kAdlerMod; b = (b + a) % kAdlerMod; }
-        return (b << 16) | a;
+        *out = (b << 16) | a;
+        return FPNGB_OK;
     }
     Context& c = g_ctx;
     std::lock_guard<std::mutex> lk(c.mu);
-    if (cudaSetDevice(c.device) != cudaSuccess) return 0;
+    FPNGB_CUDA_OK(cudaSetDevice(c.device));
     const size_t padded = align_up(size, 256), nchunks = (size + adler_chunk_bytes() - 1) / adler_chunk_bytes();
-    if (c.dev_in.reserve(padded + nchunks * 8)) return 0;
+    int rc = c.dev_in.reserve(padded + nchunks * 8); if (rc) return rc;
     uint2* dpart = (uint2*)((uint8_t*)c.dev_in.p + padded);
     std::vector<uint2> part(nchunks);
-    cudaMemcpyAsync(c.dev_in.p, data, size, cudaMemcpyHostToDevice, c.stream);
+    FPNGB_CUDA_OK(cudaMemcpyAsync(c.dev_in.p, data, size, cudaMemcpyHostToDevice, c.stream));
     launch_adler_buffer((const uint8_t*)c.dev_in.p, size, dpart, c.stream);
     count_launch(1);
-    cudaMemcpyAsync(part.data(), dpart, nchunks * 8, cudaMemcpyDeviceToHost, c.stream);
-    if (cudaStreamSynchronize(c.stream) != cudaSuccess) return 0;
+    FPNGB_CUDA_OK(cudaGetLastError());
+    FPNGB_CUDA_OK(cudaMemcpyAsync(part.data(), dpart, nchunks * 8, cudaMemcpyDeviceToHost, c.stream));
+    FPNGB_CUDA_OK(cudaStreamSynchronize(c.stream));
     unsigned long long A = a, B = b;
     for (size_t i = 0; i < nchunks; i++) {
         const unsigned long long len = (i + 1 < nchunks) ? adler_chunk_bytes() : size - i * adler_chunk_bytes();
         B = (B + (len % kAdlerMod) * A + part[i].y) % kAdlerMod;
         A = (A + part[i].x) % kAdlerMod;
     }
-    return (uint32_t)((B << 16) | A);
+    *out = (uint32_t)((B << 16) | A);
+    return FPNGB_OK;
+}
+
+uint32_t fpngb_crc32(const void* data, size_t size, uint32_t prev)
+{
+    uint32_t v = 0;
+    const int rc = fpngb_crc32_ex(data, size, prev, &v);
+    if (rc) { fprintf(stderr, "fpng_b200: fpng_crc32 failed on the device (error %d); the returned value is NOT a checksum\n", rc); return 0; }
+    return v;
+}
+
+uint32_t fpngb_adler32(const void* data, size_t size, uint32_t adler)
+{
+    uint32_t v = 0;
+    const int rc = fpngb_adler32_ex(data, size, adler, &v);
+    if (rc) { fprintf(stderr, "fpng_b200: fpng_adler32 failed on the device (error %d); the returned value is NOT a checksum\n", rc); return 0; }
+    return v;
 }
 
 int fpngb_compact_batch_device(const void* d_files, size_t stride, const uint32_t* d_sizes, uint32_t n, void* d_dst, size_t dst_cap,

@@ -20,6 +20,7 @@ struct ScanParams {
     uint32_t* hist;                               // [n*288] (histogram mode)
     uint32_t merge_first_unit;                    // RGB 1-pass: filter literal and pixel 0 share a flush unit (fpng.cpp:1187-1203)
     uint2* lane_ofs; uint32_t lane_ofs_pitch;     // v2 kernels: [n*h][pitch] per 16-pixel group: .x bit offset inside its row, .y lane_info16()
+    uint32_t lit1_rule;                           // RGBA 1-pass with a table under which fpng.cpp:1520-1528 can fire (generic kernels only)
 };
 
 struct OffsetsParams {
@@ -41,6 +42,7 @@ struct PackParams {
     uint2* row_adler;                             // rewritten for stored images (raw bytes, filter 0)
     const ImageState* st;
     uint8_t* out; size_t out_stride;
+    uint32_t lit1_rule;                           // see ScanParams
 };
 
 struct AdlerParams {

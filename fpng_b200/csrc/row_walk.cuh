@@ -96,7 +96,15 @@ struct LaneTokens {
     uint32_t tail;
     uint32_t litmask;
     uint32_t nvp;       // valid pixels in this lane (0..4)
+    uint32_t left;      // filtered pixel left of px[0] (the previous lane's / step's last pixel)
 };
+
+// Pixel value of the run that a pending match flushed at slot k (mlen[k], k = 0..3) or at the row end (k = nvp) covers:
+// the run's last pixel sits right before slot k.
+__device__ __forceinline__ uint32_t run_pixel_before(const LaneTokens& t, uint32_t k)
+{
+    return k == 0 ? t.left : (k == 1 ? t.px[0] : (k == 2 ? t.px[1] : (k == 3 ? t.px[2] : t.px[3])));
+}
 
 template <int CHANS>
 __device__ __forceinline__ void classify_step(LaneTokens& t, uint32_t p0, uint32_t w, RowCarry& carry, uint32_t lane)
@@ -105,6 +113,7 @@ __device__ __forceinline__ void classify_step(LaneTokens& t, uint32_t p0, uint32
     const uint32_t nvp = t.nvp;
     uint32_t left = __shfl_up_sync(kFullMask, t.px[3], 1);
     if (lane == 0) left = carry.prev_px;
+    t.left = left;
 
     uint32_t eqmask = 0;
     if (nvp > 0 && p0 > 0 && t.px[0] == left) eqmask |= 1u;

@@ -49,6 +49,17 @@ struct Context {
 };
 
 
+// a fixed set of timing-less events that is destroyed on every exit path of the pipelined host entry points
+template <int N>
+struct EventSet {
+    cudaEvent_t ev[N];
+    bool ok = true;
+    EventSet() { for (int i = 0; i < N; i++) { ev[i] = nullptr; if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) ok = false; } }
+    ~EventSet() { for (int i = 0; i < N; i++) if (ev[i]) cudaEventDestroy(ev[i]); }
+    EventSet(const EventSet&) = delete;
+    EventSet& operator=(const EventSet&) = delete;
+};
+
 Context& context();
 void count_launch(uint64_t n);
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

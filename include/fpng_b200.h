@@ -109,12 +109,20 @@ FPNGB_API int fpngb_decode_batch_host(const void* const* files, const uint32_t* 
 FPNGB_API int fpngb_get_info_ex(const void* file, uint32_t size, uint32_t* w, uint32_t* h, uint32_t* chans,
                                 uint32_t* idat_ofs, uint32_t* idat_len);
 
-/* Replace fpng::fpng_crc32 / fpng::fpng_adler32 (src/fpng.h:26-31).  Host buffers; computed with the device kernels. */
+/* Replace fpng::fpng_crc32 / fpng::fpng_adler32 (src/fpng.h:26-31).  Host buffers.  Buffers of 4 KiB and more are
+ * checksummed by the device kernels.  NOTE (the one host-side arithmetic in this library): shorter buffers, and any
+ * call made before fpngb_init(), use the small host CRC/Adler routines the container code needs anyway for the 17-byte
+ * IHDR and the chunk walk -- a kernel launch for a few dozen bytes would only add latency.  The reference signatures
+ * cannot report errors and 0 is a valid checksum, so a device failure is reported on stderr and 0 is returned; use the
+ * _ex forms (0 = OK, otherwise an FPNGB_ERR_* / 1000 + cudaError code) to detect failures programmatically. */
 FPNGB_API uint32_t fpngb_crc32(const void* data, size_t size, uint32_t prev_crc32);
 FPNGB_API uint32_t fpngb_adler32(const void* data, size_t size, uint32_t adler);
+FPNGB_API int fpngb_crc32_ex(const void* data, size_t size, uint32_t prev_crc32, uint32_t* out);
+FPNGB_API int fpngb_adler32_ex(const void* data, size_t size, uint32_t adler, uint32_t* out);
 
 /* Packs the n variable-size files of a batch (d_files + i*stride, d_sizes[i]) back to back into d_dst, each file
- * starting 16-byte aligned; d_offsets receives n+1 byte offsets (offsets[n] = total).  New (no reference counterpart):
+ * starting 16-byte aligned; d_offsets receives n+1 byte offsets (offsets[n] = total; bit 63 of offsets[n] is set when
+ * dst_cap was too small -- files that did not fit are not copied).  New (no reference counterpart):
  * the staging step before the single NCCL gather of a rank's encoded shard (BASELINE.json north_star). */
 FPNGB_API int fpngb_compact_batch_device(const void* d_files, size_t stride, const uint32_t* d_sizes, uint32_t n,
                                          void* d_dst, size_t dst_cap, uint64_t* d_offsets, void* stream);

@@ -19,6 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libfpng_ref.so")
 REF_TRAIN_SO = os.path.join(HERE, "_ref", "libfpng_ref_train.so")
+REF_PATCH_SO = os.path.join(HERE, "_ref", "libfpng_ref_patch.so")
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -31,7 +32,8 @@ def build(force: bool = False) -> None:
     ref_possible = os.path.exists("/root/reference/src/fpng.cpp")
     ref_stale = ref_possible and (
         (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_shim.cpp"))
-        or (not os.path.exists(REF_TRAIN_SO)) or os.path.getmtime(REF_TRAIN_SO) < os.path.getmtime(os.path.join(HERE, "ref_train_shim.cpp")))
+        or (not os.path.exists(REF_TRAIN_SO)) or os.path.getmtime(REF_TRAIN_SO) < os.path.getmtime(os.path.join(HERE, "ref_train_shim.cpp"))
+        or (not os.path.exists(REF_PATCH_SO)) or os.path.getmtime(REF_PATCH_SO) < os.path.getmtime(os.path.join(HERE, "ref_patch_shim.cpp")))
     if force or stale or ref_stale:
         subprocess.check_call(["make", "-s", "-f", os.path.join(HERE, "Makefile"), "all"], cwd=HERE)
 
@@ -66,8 +68,15 @@ class Oracle:
         L.oracle_get_info.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, u32p]
         L.oracle_static_table.restype = None
         L.oracle_static_table.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, u32p]
+        L.oracle_set_static_table.restype = C.c_int
+        L.oracle_set_static_table.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]
         L.oracle_init()
         self.L = L
+
+    def set_static_table(self, chans, prefix: bytes = b"", bit_buf: int = 0, bit_buf_size: int = 0) -> bool:
+        """Install a trained 1-pass table (or restore the shipped one with an empty prefix)."""
+        a = np.frombuffer(bytes(prefix), dtype=np.uint8) if prefix else np.zeros(1, np.uint8)
+        return bool(self.L.oracle_set_static_table(chans, _ptr(a), len(prefix), bit_buf, bit_buf_size))
 
     def crc32(self, data, prev=0) -> int:
         a = _as_u8(data)
@@ -264,3 +273,54 @@ class RefTrainer:
         ok = self.L.reft_create_prefix(_ptr(counts), chans, _ptr(prefix), prefix.size, C.byref(n), C.byref(bb), C.byref(bs), _ptr(codes), _ptr(sizes))
         assert ok
         return prefix[: n.value].tobytes(), bb.value, bs.value, codes, sizes
+
+
+class RefPatched:
+    """The reference encoder with its static 1-pass tables patchable in memory (oracle/ref_patch_shim.cpp): every line of
+    the encoder is the reference's, only the table contents change.  Prefix length must equal the reference's own
+    compile-time table size (62 bytes RGB / 61 bytes RGBA)."""
+
+    @staticmethod
+    def available() -> bool:
+        try:
+            build()
+        except Exception:
+            pass
+        return os.path.exists(REF_PATCH_SO)
+
+    def __init__(self):
+        if not RefPatched.available():
+            raise RuntimeError("oracle/_ref/libfpng_ref_patch.so is not built")
+        L = C.CDLL(REF_PATCH_SO)
+        L.refp_table_len.restype = C.c_uint32
+        L.refp_table_len.argtypes = [C.c_uint32]
+        L.refp_set_table.restype = C.c_int
+        L.refp_set_table.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.refp_reset_table.argtypes = [C.c_uint32]
+        L.refp_encode.restype = C.c_size_t
+        L.refp_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
+        L.refp_decode.restype = C.c_int
+        L.refp_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, u32p, u32p, u32p, C.c_uint32]
+        L.refp_init()
+        self.L = L
+
+    def table_len(self, chans) -> int:
+        return self.L.refp_table_len(chans)
+
+    def set_table(self, chans, prefix: bytes, bit_buf: int, bit_buf_size: int, codes, sizes) -> bool:
+        pre = np.frombuffer(bytes(prefix), dtype=np.uint8).copy()
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint8)
+        return bool(self.L.refp_set_table(chans, _ptr(pre), pre.size, bit_buf, bit_buf_size, _ptr(codes), _ptr(sizes)))
+
+    def reset_table(self, chans) -> None:
+        self.L.refp_reset_table(chans)
+
+    def encode(self, img, w, h, chans, flags=0) -> bytes:
+        a = _as_u8(img).copy()
+        cap = 58 + 6 + (w * chans + 1) * h + 5 * (((w * chans + 1) * h + 65534) // 65535) + 16 + 64
+        out = np.empty(cap, dtype=np.uint8)
+        n = self.L.refp_encode(_ptr(a), w, h, chans, flags, _ptr(out), cap)
+        if n == 0 or n > cap:
+            raise ValueError("patched reference encoder failed")
+        return out[:n].tobytes()

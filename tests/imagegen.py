@@ -79,3 +79,37 @@ def make(kind: str, w: int, h: int, chans: int, index: int = 0) -> np.ndarray:
     if kind == "zero":
         return np.zeros((h, w, chans), np.uint8)
     raise KeyError(kind)
+
+
+def from_deltas(delta: np.ndarray) -> np.ndarray:
+    """Image whose Up-filtered rows (row 0: raw) equal `delta` (h, w, chans): running byte-wise sum down the rows."""
+    return (np.cumsum(delta.astype(np.uint32), axis=0) & 255).astype(np.uint8)
+
+
+def short_runs(w: int, h: int, chans: int, seed: int, palette) -> np.ndarray:
+    """Filtered-domain pixels drawn channel-wise from `palette` with many runs of exactly 1-3 equal pixels: exercises the
+    RGBA 1-pass "one-pixel match vs four literals" decision (src/fpng.cpp:1520-1528) in both directions."""
+    rs = np.random.RandomState(seed)
+    pal = np.asarray(palette, dtype=np.uint8)
+    d = pal[rs.randint(0, len(pal), size=(h, w, chans))]
+    rep = rs.rand(h, w) < 0.45
+    for y in range(h):
+        for x in range(1, w):
+            if rep[y, x]:
+                d[y, x] = d[y, x - 1]
+    return from_deltas(d)
+
+
+def trained_table_images(chans: int, sizes):
+    """The fixed image set of tests/golden/trained_tables.json (name, w, h, pixels), built from the table's code sizes so
+    that cheap and expensive literals both occur next to one-pixel matches."""
+    order = np.argsort(np.asarray(sizes)[:256], kind="stable")
+    cheap = [int(v) for v in order[:5]]
+    pal_mixed = cheap + [int(order[40]), int(order[200])]
+    out = []
+    for i, (w, h, pal) in enumerate([(64, 20, cheap[:2]), (257, 9, cheap), (96, 33, pal_mixed), (16, 5, cheap[:1]), (130, 12, pal_mixed)]):
+        out.append((f"short_runs_{i}", w, h, short_runs(w, h, chans, 100 + i, pal)))
+    out.append(("g1", 128, 16, make("g1", 128, 16, chans, 3)))
+    out.append(("runs", 200, 11, make("runs", 200, 11, chans, 5)))
+    out.append(("zero", 70, 7, make("zero", 70, 7, chans, 0)))
+    return out

@@ -144,8 +144,7 @@ def test_full_size_configs_properties(gpu, ref):
             assert len(raw) == (w * c + 1) * h
             st, px, *_ = ref.decode(png, c)
             assert st == 0 and np.array_equal(px, imgs[i].reshape(-1))
-            if flags == 0:
-                assert png == ref.encode(imgs[i], w, h, c, flags)
+            assert png == ref.encode(imgs[i], w, h, c, flags)        # 1-pass and 2-pass alike (C4 = 2048^2, FPNG_ENCODE_SLOWER)
 
 
 def test_checksum_utilities(gpu, oracle):
