@@ -333,8 +333,8 @@ def run_ours(args, wl):
     clocks = sampler.stop(wall0, wall1)
     launches = fpng_b200.launch_count() - launches0
     ms = e0.elapsed_time(e1)
-    prof = (C.c_float * 7)()
-    L.fpngb_profile_read(prof, 7)
+    prof = (C.c_float * 9)()
+    L.fpngb_profile_read(prof, 9)
     L.fpngb_profile_enable(0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -345,10 +345,12 @@ def run_ours(args, wl):
 
     out_bytes = int((sizes.to(torch.int64) & 0xFFFFFFFF).sum().item())
     in_bytes = n * w * h * c
-    names = ["hist", "huffman", "scan", "offsets", "pack", "adler", "crc"]
+    names = ["hist", "huffman", "scan", "offsets", "fused", "finish", "pack", "adler", "crc"]
     kern = {k: float(v) for k, v in zip(names, prof)}
     peak, peak_src = measured_peak()
-    algo = {"hist": in_bytes, "huffman": 0, "scan": in_bytes, "offsets": 0, "pack": in_bytes + out_bytes, "adler": 0, "crc": out_bytes}
+    fused_path = kern["fused"] > 0
+    algo = {"hist": in_bytes, "huffman": 0, "scan": in_bytes, "offsets": 0, "fused": in_bytes + out_bytes, "finish": 0,
+            "pack": 0 if fused_path else in_bytes + out_bytes, "adler": 0, "crc": out_bytes}
     dominant = max(kern, key=lambda k: kern[k])
 
     # DRAM traffic per launch from the committed `ncu --set full` capture of the same workload (profiles/traffic.json,
@@ -366,6 +368,7 @@ def run_ours(args, wl):
     def roof(k):
         gbs = algo[k] / 1e9 / (kern[k] / 1e3) if kern[k] > 0 else 0.0
         return {"kernel": k, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic_of(k),
+                "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture (profiles/traffic.json), scaled by images per launch; not measured in this run",
                 "ms_per_launch": kern[k], "algorithmic_bytes_per_launch": algo[k], "peak_source": peak_src}
 
     line = {
@@ -374,9 +377,11 @@ def run_ours(args, wl):
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": wl["name"], "kind": args.kind, "images_per_gpu": n, "w": w, "h": h, "chans": c, "flags": flags,
                    "l2": "inputs larger than L2 (%.0f MB per step)" % (in_bytes / 1e6) if in_bytes > 126e6 else "input smaller than L2: L2-warm",
-                   "out_over_in": out_bytes / in_bytes, "parity_image0_vs_oracle": parity},
+                   "out_over_in": out_bytes / in_bytes, "parity_image0_vs_oracle": parity,
+                   "g1_noise": "gradient + uniform integer noise in [-3, 3] from numpy RandomState(1234 + i % 16).randint (MT19937; SURVEY 8d words it as std::mt19937(1234 + i): same engine, different integer mapping, 16 distinct noise fields per batch); both arms use this generator"},
         "clocks": clocks, "gpu_launches": int(launches),
-        "kernels_ms": kern, "roofline": roof(dominant), "roofline_scan": roof("scan"),
+        "kernels_ms": kern, "roofline": roof(dominant), "roofline_scan": roof("fused" if fused_path else "scan"),
+        "encoder": "single-pass fused kernel (encode_fused.cu: filter + match + code emission + bit placement in one read of the pixels)" if fused_path else "two-kernel scan + pack",
         "whole_step": {"algorithmic_gbs": (in_bytes + out_bytes) / 1e9 / (ms / args.steps / 1e3),
                        "frac_of_peak": (in_bytes + out_bytes) / 1e9 / (ms / args.steps / 1e3) / peak},
     }
@@ -385,6 +390,20 @@ def run_ours(args, wl):
     if not args.no_decode:
         sz_host = (sizes.cpu().numpy().astype(np.int64) & 0xFFFFFFFF)
         files = [bytes(out[i, : int(sz_host[i])].cpu().numpy()) for i in range(n)]
+        dec_input = "this rank's GPU-encoded files, device resident"
+        # BASELINE config 5 decodes REFERENCE-written files: write them with the unmodified reference encoder (oracle/_ref)
+        # on the host threads, outside every timed region; they must equal the GPU-written files byte for byte.
+        from oracle.pyoracle import Ref
+        if Ref.available() and not args.own_files:
+            from concurrent.futures import ThreadPoolExecutor
+            rref = Ref()
+            host_batch = batch.cpu().numpy()
+            with ThreadPoolExecutor(max_workers=max(1, host_cores() // max(1, world))) as ex:
+                ref_files = list(ex.map(lambda i: rref.encode(host_batch[i], w, h, c, flags), range(n)))
+            same = sum(a == b for a, b in zip(files, ref_files))
+            files = ref_files
+            dec_input = f"reference-written files (unmodified reference encoder, oracle/_ref), device resident; {same}/{n} byte-identical to the GPU-written files"
+            del host_batch
         files_dev, fstride, fsizes, fofs, flens, ww, hh, cc = fpng_b200.pack_files_for_device(files, dev)
         px = torch.empty((n, h, w, c), dtype=torch.uint8, device=dev)
         status = torch.empty((n,), dtype=torch.int32, device=dev)
@@ -413,7 +432,7 @@ def run_ours(args, wl):
         line["decode"] = {"value": world * n * w * h / MP / (dms / 1e3), "unit": "MP/s", "ms_per_step": dms, "steps": dsteps,
                           "pixels_match_input": dec_ok, "algorithmic_gbs": dec_bytes / 1e9 / (dms / 1e3),
                           "frac_of_peak": dec_bytes / 1e9 / (dms / 1e3) / peak,
-                          "input": "this rank's GPU-encoded files (byte-identical to reference-written files), device resident"}
+                          "input": dec_input}
         # end to end through the C ABI with host buffers: files (pinned) -> H2D -> kernels -> D2H pixels (pinned)
         hfiles = torch.zeros((n, fstride), dtype=torch.uint8).pin_memory()
         hfiles.copy_(files_dev.cpu())
@@ -442,25 +461,73 @@ def run_ours(args, wl):
                                  "pixels_match_input": bool(torch.equal(hpx.view(n, h, w, c), batch.cpu()))}
         del files_dev, px, hfiles, hpx
 
-    # ---- the one NCCL gather of the encoded buffers (north_star), timed separately from the per-rank encode
+    # ---- the ONE gather of the encoded buffers (north_star) through the C ABI (fpngb_gather_encoded_device: sizes
+    # all-gather + peer-window push over NVLink + 4-byte completion all-reduce).  Three numbers: the gather alone, and the
+    # whole job "encode + gather to rank 0" timed barrier to barrier (value_with_gather), plus the all-gather form.
     if world > 1:
-        from fpng_b200.dist import gather_encoded
-        gather_encoded(out, sizes, 0)
+        import hashlib
+        from fpng_b200 import dist as fd
+        fd.init_comm()
+        window_bytes = world * n * stride
+        fd.gather_setup(window_bytes, n)
+        _, _, _, p2p = fd.comm_info()
+        ptrs = fd.gather_encoded_device(out, sizes, dst_rank=0, stream=stream.cuda_stream)
         torch.cuda.synchronize(dev)
         dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        res = gather_encoded(out, sizes, 0)
-        g1.record(stream)
-        torch.cuda.synchronize(dev)
-        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        # verify on hardware what rank 0 received: sha256 of the first and last file of every rank's shard against the
+        # oracle's encoding of those images (rank 0 regenerates them), plus every size against the senders' own sizes
+        gather_ok = None
+        all_sz = [torch.zeros((n,), dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.all_gather(all_sz, sizes)
+        if rank == 0:
+            from oracle.pyoracle import Oracle
+            orc = Oracle()
+            win, offs, alls = fd.gathered_views(*ptrs, window_bytes, world, n, dev)
+            offs_h = offs.cpu().numpy(); alls_h = alls.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            gather_ok = (int(offs_h[-1]) >> 63) == 0
+            for r in range(world):
+                gather_ok = gather_ok and bool(np.array_equal(alls_h[r * n:(r + 1) * n], all_sz[r].cpu().numpy().astype(np.int64) & 0xFFFFFFFF))
+                for i in (0, n - 1):
+                    o0, sz = int(offs_h[r * n + i]), int(alls_h[r * n + i])
+                    got = hashlib.sha256(win[o0:o0 + sz].cpu().numpy().tobytes()).hexdigest()
+                    exp = hashlib.sha256(orc.encode(workload_image(wl, args.kind, r * n + i), w, h, c, flags)).hexdigest()
+                    gather_ok = gather_ok and got == exp
         tb = torch.tensor([float(out_bytes)], dtype=torch.float64, device=dev)
         dist.all_reduce(tb)
-        line["gather"] = {"ms": float(tg.item()), "bytes_total": float(tb.item()), "to_rank": 0,
-                          "gbs_into_rank0": (float(tb.item()) - out_bytes) / 1e9 / (float(tg.item()) / 1e3) if rank == 0 else None,
-                          "what": "all_gather(sizes) + compact kernel + grouped send/recv of every rank's encoded shard to rank 0 over NCCL"}
-        del res
+        total_bytes = float(tb.item())
+
+        def timed(fn, reps):
+            dist.barrier(); torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            tt = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        greps = max(1, min(args.steps, 10))
+        g_ms = timed(lambda: fd.gather_encoded_device(out, sizes, dst_rank=0, stream=stream.cuda_stream), greps)
+        ag_ms = timed(lambda: fd.gather_encoded_device(out, sizes, dst_rank=-1, stream=stream.cuda_stream), greps)
+
+        def step_with_gather():
+            step()
+            fd.gather_encoded_device(out, sizes, dst_rank=0, stream=stream.cuda_stream)
+
+        sg_ms = timed(step_with_gather, greps)
+        line["gather"] = {"ms": g_ms, "bytes_total": total_bytes, "to_rank": 0, "path": "peer-window push over NVLink (CUDA IPC)" if p2p else "NCCL grouped send/recv fallback",
+                          "gbs_into_rank0": (total_bytes - total_bytes / world) / 1e9 / (g_ms / 1e3),
+                          "nvlink_ingress_reference_gbs": 770.0, "frac_of_nvlink_ingress": (total_bytes - total_bytes / world) / 1e9 / (g_ms / 1e3) / 770.0,
+                          "allgather_ms": ag_ms, "allgather_gbs_into_each_rank": (total_bytes - total_bytes / world) / 1e9 / (ag_ms / 1e3),
+                          "bytes_verified_on_rank0": gather_ok,
+                          "what": "fpngb_gather_encoded_device (C ABI): ncclAllGather(sizes) + offsets kernel + every rank stores its files into rank 0's window + 4-byte all-reduce; no host sync"}
+        line["value_with_gather"] = {"value": world * n * w * h / MP / (sg_ms / 1e3), "unit": "MP/s", "ms_per_step": sg_ms, "steps": greps,
+                                     "what": "encode of every rank's shard + the gather of all encoded files to rank 0, barrier to barrier, max over ranks",
+                                     "limiter": "rank 0's NVLink ingress (one receiver)" if g_ms > 0.5 * (ms / args.steps) else "encode kernels"}
+        fd.destroy_comm()
 
     # ---- end to end through the C ABI with host (pinned) buffers: H2D + kernels + D2H inside the timed region
     n_e2e = min(n, args.e2e_images) if args.e2e_images else n
@@ -532,14 +599,18 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS),
+                    help="auto: C2 (BASELINE config 2, the 1-GPU configuration) at --gpus 1, C3 (config 3, the north-star 8-GPU configuration) at --gpus > 1")
     ap.add_argument("--kind", default="g1", choices=["g0", "g1", "g2"])
     ap.add_argument("--images", type=int, default=0, help="images per GPU (default: the workload's)")
     ap.add_argument("--e2e-images", type=int, default=0, help="images per e2e step (0 = the whole per-GPU batch)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--own-files", action="store_true", help="decode leg: use the GPU-written files instead of reference-written ones")
     args = ap.parse_args()
+    if args.workload == "auto":
+        args.workload = "c2" if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) <= 1 else "c3"
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)

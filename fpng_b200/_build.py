@@ -13,6 +13,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3", "-shared",
 ]
+# comm.cu talks to NCCL (system libnccl.so.2 2.27.3; inside a torch process the already loaded, ABI-compatible bundled one is used)
+LINK_FLAGS = ["-lnccl"]
 
 
 def sources() -> list[str]:
@@ -34,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + LINK_FLAGS
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

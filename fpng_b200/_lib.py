@@ -64,6 +64,24 @@ def lib() -> C.CDLL:
     L.fpngb_host_alloc.argtypes = [C.c_size_t]
     L.fpngb_host_free.restype = None
     L.fpngb_host_free.argtypes = [C.c_void_p]
+    L.fpngb_crc32_ex.restype = C.c_int
+    L.fpngb_crc32_ex.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, u32p]
+    L.fpngb_adler32_ex.restype = C.c_int
+    L.fpngb_adler32_ex.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, u32p]
+    L.fpngb_comm_unique_id.restype = C.c_int
+    L.fpngb_comm_unique_id.argtypes = [C.c_void_p]
+    L.fpngb_comm_init.restype = C.c_int
+    L.fpngb_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.fpngb_comm_adopt.restype = C.c_int
+    L.fpngb_comm_adopt.argtypes = [C.c_void_p]
+    L.fpngb_comm_destroy.restype = C.c_int
+    L.fpngb_comm_info.restype = C.c_int
+    L.fpngb_comm_info.argtypes = [C.POINTER(C.c_int)] * 3
+    L.fpngb_gather_setup.restype = C.c_int
+    L.fpngb_gather_setup.argtypes = [C.c_size_t, C.c_uint32]
+    L.fpngb_gather_encoded_device.restype = C.c_int
+    L.fpngb_gather_encoded_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     L.fpngb_launch_count.restype = C.c_uint64
     L.fpngb_debug_rows_per_warp.restype = None
     L.fpngb_debug_rows_per_warp.argtypes = [C.c_uint32]
@@ -81,7 +99,11 @@ _ERR = {1: "invalid argument", 2: "output buffer too small", 3: "fpng_init() has
         4: "no CUDA device (this package has no CPU fallback)", 5: "pointer/stride alignment", 6: "internal error"}
 
 
+def _nccl_msg(rc: int) -> str:
+    return f"NCCL error {rc - 2000}"
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
-        msg = _ERR.get(rc, f"CUDA error {rc - 1000}" if rc >= 1000 else f"code {rc}")
+        msg = _ERR.get(rc, _nccl_msg(rc) if rc >= 2000 else (f"CUDA error {rc - 1000}" if rc >= 1000 else f"code {rc}"))
         raise FpngB200Error(f"{what}: {msg}")

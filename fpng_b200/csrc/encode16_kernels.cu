@@ -314,6 +314,7 @@ __device__ __forceinline__ void put_event16(BitStager16& bs, uint32_t s_match_sa
 template <int CHANS>
 __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParams p, uint32_t rows_per_warp)
 {
+    if (p.stored_only && !p.st[blockIdx.y].stored) return;     // after the fused encoder only stored-block images are left to write
     constexpr uint32_t M = max_match_pixels(CHANS);
     constexpr int kHalfWords = 2 * CHANS;        // filtered words of 8 pixels
     extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -518,9 +519,6 @@ bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t
 template <int CHANS> constexpr size_t scan16_smem() { return kScan16Rows * Walk16<CHANS>::kWarpBytes + 256 + 96; }
 template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk16<CHANS>::kWarpBytes + (512 + 88 + kPack16Rows * stage16_words<CHANS>()) * 4; }
 
-// opt in to > 48 KiB of dynamic shared memory (per kernel instantiation, once per process)
-#define FPNGB_SET_SMEM(kernel, bytes) do { static bool done_ = false; \
-    if (!done_) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); done_ = true; } } while (0)
 
 void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {

@@ -22,6 +22,7 @@
 namespace fpngb {
 
 static std::atomic<uint64_t> g_launches{0};
+static bool g_no_fused_override = false;       // fpngb_debug_disable_fused(): tests run both encoders in one process
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -143,7 +144,7 @@ static std::mutex g_init_mu;
 Context& context() { return g_ctx; }
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
-enum ProfSlot { kProfHist = 0, kProfHuff, kProfScan, kProfOffsets, kProfPack, kProfAdler, kProfCrc, kProfSlots };
+enum ProfSlot { kProfHist = 0, kProfHuff, kProfScan, kProfOffsets, kProfFused, kProfFinish, kProfPack, kProfAdler, kProfCrc, kProfSlots };
 struct ProfSet { cudaEvent_t ev[kProfSlots + 1]; bool used[kProfSlots]; };
 static bool g_profile = false;
 static std::vector<ProfSet*> g_prof_sets;      // one per encode call since the last read
@@ -174,10 +175,11 @@ static void prof_mark(ProfSet* ps, int slot, cudaStream_t s)
 struct Workspace {
     uint32_t* row_bits; uint2* row_adler; unsigned long long* row_ofs; ImageState* st; uint32_t* hist; CodeBook* books;
     uint2* lane_ofs; uint32_t lane_ofs_pitch;
+    void* fused_desc;
 };
 
 
-static int carve_workspace(Context& c, uint32_t n, uint32_t h, uint32_t width, bool two_pass, Workspace& w)
+static int carve_workspace(Context& c, uint32_t n, uint32_t h, uint32_t width, bool two_pass, Workspace& w, bool fused = false)
 {
     const size_t rows = (size_t)n * h;
     const uint32_t lane_pitch = ((width + 511u) / 512u) * 32u;       // one uint2 per 16-pixel group, whole warp steps
@@ -188,13 +190,15 @@ static int carve_workspace(Context& c, uint32_t n, uint32_t h, uint32_t width, b
     const size_t o_st = o; o = align_up(o + (size_t)n * sizeof(ImageState), 256);
     const size_t o_hist = o; o = align_up(o + (two_pass ? (size_t)n * 288 * 4 : 0), 256);
     const size_t o_books = o; o = align_up(o + (two_pass ? (size_t)n * sizeof(CodeBook) : 0), 256);
-    const size_t o_lane = o; o = align_up(o + rows * lane_pitch * 8, 256);
+    const size_t o_lane = o; o = align_up(o + (fused ? 0 : rows * lane_pitch * 8), 256);
+    const size_t o_desc = o; o = align_up(o + (fused ? fused_desc_bytes(n, width, h) : 0), 256);
     int rc = c.ws.reserve(o);
     if (rc) return rc;
     uint8_t* b = (uint8_t*)c.ws.p;
     w.row_bits = (uint32_t*)(b + o_bits); w.row_adler = (uint2*)(b + o_adl); w.row_ofs = (unsigned long long*)(b + o_ofs);
     w.st = (ImageState*)(b + o_st); w.hist = (uint32_t*)(b + o_hist); w.books = (CodeBook*)(b + o_books);
     w.lane_ofs = (uint2*)(b + o_lane); w.lane_ofs_pitch = lane_pitch;
+    w.fused_desc = b + o_desc;
     return 0;
 }
 
@@ -242,19 +246,22 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
                                uint32_t chans, uint32_t flags, uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, cudaStream_t s)
 {
     const bool two_pass = (flags & FPNGB_ENCODE_SLOWER) && !(flags & FPNGB_FORCE_UNCOMPRESSED);
-    Workspace ws;
-    int rc = carve_workspace(c, n, h, w, two_pass, ws);
-    if (rc) return rc;
-    rc = c.ws_acquire(s);
-    if (rc) return rc;
-    const int mode = pick_load_mode(d_pixels, image_stride, w, chans);
     // second-generation kernels (16 pixels per lane, coalesced 128-bit loads) whenever every scanline is 16-byte aligned;
     // FPNGB_FORCE_GENERIC=1 keeps the generic kernels (tests compare both)
     static const bool force_generic = getenv("FPNGB_FORCE_GENERIC") && atoi(getenv("FPNGB_FORCE_GENERIC")) != 0;
+    static const bool no_fused = getenv("FPNGB_NO_FUSED") && atoi(getenv("FPNGB_NO_FUSED")) != 0;
     // RGBA 1-pass under a table where a one-pixel match can lose against four literals: only the generic kernels
     // implement the reference's check (fpng.cpp:1520-1528); it cannot fire with the shipped table
     const uint32_t lit1_rule = (!two_pass && chans == 4 && c.h_static_books[1].lit1_rule) ? 1u : 0u;
     const bool v2 = !force_generic && !lit1_rule && walk16_eligible(d_pixels, image_stride, w, chans);
+    // third generation: single pass over the pixels (encode_fused.cu) for every shape it covers (w <= 4096, aligned scanlines)
+    const bool fused = v2 && !no_fused && !g_no_fused_override && !(flags & FPNGB_FORCE_UNCOMPRESSED) && fused_eligible(d_pixels, image_stride, w, h, chans, n);
+    Workspace ws;
+    int rc = carve_workspace(c, n, h, w, two_pass, ws, fused);
+    if (rc) return rc;
+    rc = c.ws_acquire(s);
+    if (rc) return rc;
+    const int mode = pick_load_mode(d_pixels, image_stride, w, chans);
     const CodeBook* books = two_pass ? ws.books : c.d_static_books + (chans == 4 ? 1 : 0);
     const uint32_t book_stride = two_pass ? 1u : 0u;
 
@@ -276,6 +283,24 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
         prof_mark(ps, kProfHuff, s);
         count_launch(2);
     }
+    PackParams pp{};
+    pp.pixels = d_pixels; pp.image_stride = image_stride; pp.w = w; pp.h = h; pp.books = books; pp.book_stride = book_stride;
+    pp.row_ofs = ws.row_ofs; pp.row_bits = ws.row_bits; pp.lane_ofs = ws.lane_ofs; pp.lane_ofs_pitch = ws.lane_ofs_pitch; pp.row_adler = ws.row_adler; pp.st = ws.st; pp.out = d_out; pp.out_stride = out_stride;
+    pp.lit1_rule = lit1_rule;
+    if (fused) {
+        uint8_t png_header[kPngHeaderSize];
+        make_png_header(png_header, w, h, chans);
+        cudaEvent_t mid = ps ? ps->ev[kProfFused + 1] : nullptr;
+        rc = launch_encode_fused(d_pixels, image_stride, n, w, h, chans, flags, books, book_stride, ws.row_adler, ws.st, ws.fused_desc,
+                                 d_out, out_stride, d_sizes, png_header, sp.merge_first_unit, s, mid);
+        if (rc) return rc;
+        if (ps) ps->used[kProfFused] = true;
+        prof_mark(ps, kProfFinish, s);
+        pp.stored_only = 1u;
+        launch_pack16(pp, n, chans, s);                                     // stored-block images only (fpng.cpp:1728-1758)
+        prof_mark(ps, kProfPack, s);
+        count_launch(1);                                                    // + the 4 counted below = fused, finish, pack, adler, crc
+    } else {
     if (v2) launch_scan16(sp, n, chans, s); else launch_scan(sp, n, chans, mode, false, s);
     prof_mark(ps, kProfScan, s);
 
@@ -286,12 +311,10 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     launch_offsets(op, n, s);
     prof_mark(ps, kProfOffsets, s);
 
-    PackParams pp{};
-    pp.pixels = d_pixels; pp.image_stride = image_stride; pp.w = w; pp.h = h; pp.books = books; pp.book_stride = book_stride;
-    pp.row_ofs = ws.row_ofs; pp.row_bits = ws.row_bits; pp.lane_ofs = ws.lane_ofs; pp.lane_ofs_pitch = ws.lane_ofs_pitch; pp.row_adler = ws.row_adler; pp.st = ws.st; pp.out = d_out; pp.out_stride = out_stride;
-    pp.lit1_rule = lit1_rule;
     if (v2) launch_pack16(pp, n, chans, s); else launch_pack(pp, n, chans, mode, s);
     prof_mark(ps, kProfPack, s);
+    count_launch(1);
+    }
 
     AdlerParams ap{ws.row_adler, ws.st, d_out, out_stride, w, h, chans};
     launch_adler_finalize(ap, n, s);
@@ -302,7 +325,7 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     cp.max_tiles = crc_ctas_for(max_encoded_size(w, h, chans)); cp.msg_start = kPngHeaderSize - 4; cp.init_xor = 0xFFFFFFFFu;
     launch_crc(cp, n, s);
     prof_mark(ps, kProfCrc, s);
-    count_launch(5);
+    count_launch(4);
     FPNGB_CUDA_OK(cudaGetLastError());
     return c.ws_release(s);
 }
@@ -349,6 +372,9 @@ size_t fpngb_max_encoded_size(uint32_t w, uint32_t h, uint32_t chans) { return m
 
 // test hook: scanlines per warp of the 16-pixel scan/pack kernels (0 = automatic); not part of the reference surface
 FPNGB_API void fpngb_debug_rows_per_warp(uint32_t v) { set_rows_per_warp16(v); }
+
+// test hook: 1 = use the two-kernel (scan + pack) encoder even where the single-pass encoder applies; not part of the reference surface
+FPNGB_API void fpngb_debug_disable_fused(int off) { g_no_fused_override = off != 0; }
 
 // exposes the static code books to the tests (sizes[288], codes[288]); not part of the reference surface
 FPNGB_API int fpngb_debug_static_table(uint32_t chans, uint8_t* sizes, uint16_t* codes, uint32_t* hdr_bits)

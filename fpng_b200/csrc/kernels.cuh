@@ -43,6 +43,7 @@ struct PackParams {
     const ImageState* st;
     uint8_t* out; size_t out_stride;
     uint32_t lit1_rule;                           // see ScanParams
+    uint32_t stored_only;                         // 16-pixel pack kernel: only write images that fell back to stored blocks (fused encoder ran before)
 };
 
 struct AdlerParams {
@@ -65,6 +66,18 @@ struct HuffParams {
     uint32_t chans;
     uint32_t training;                            // 1: table training (fpng.cpp:909-988): symbol 256 keeps its own count in the scaling
 };
+
+// opt in to > 48 KiB of dynamic shared memory (per kernel instantiation, once per process)
+#define FPNGB_SET_SMEM(kernel, bytes) do { static bool done_ = false; \
+    if (!done_) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); done_ = true; } } while (0)
+
+// third-generation single-pass encoder (encode_fused.cu)
+bool fused_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t h, uint32_t chans, uint32_t n);
+size_t fused_desc_bytes(uint32_t n, uint32_t w, uint32_t h);
+int launch_encode_fused(const uint8_t* pixels, size_t image_stride, uint32_t n, uint32_t w, uint32_t h, uint32_t chans, uint32_t flags,
+                        const CodeBook* books, uint32_t book_stride, uint2* row_adler, ImageState* st, void* desc_mem,
+                        uint8_t* out, size_t out_stride, uint32_t* sizes, const uint8_t* png_header, uint32_t merge_first_unit, cudaStream_t s,
+                        cudaEvent_t mid_event);
 
 void launch_scan(const ScanParams& p, uint32_t n, uint32_t chans, int mode, bool hist, cudaStream_t s);
 bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t chans);

@@ -91,3 +91,72 @@ def gather_encoded(out, sizes, dst_rank: int = 0, group=None):
     for w in (dist.batch_isend_irecv(ops) if ops else []):
         w.wait()
     return results
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The C-ABI communicator (include/fpng_b200.h "multi-GPU"): NCCL communicator owned by the library + peer-window gather.
+# torch.distributed is only the out-of-band channel that carries the 128-byte ncclUniqueId to every rank.
+# ---------------------------------------------------------------------------------------------------------------------
+class _DevArray:
+    """Zero-copy view of library-owned device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, nbytes: int, typestr: str, itemsize: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def init_comm(group=None) -> None:
+    """Collective over `group`: creates the library's own NCCL communicator (fpngb_comm_init) on the fpng_init() device."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    idbuf = np.zeros(128, dtype=np.uint8)
+    if rank == 0:
+        check(lib().fpngb_comm_unique_id(idbuf.ctypes.data_as(C.c_void_p)), "comm_unique_id")
+    t = torch.from_numpy(idbuf).to(dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    idbuf = t.cpu().numpy().copy()
+    check(lib().fpngb_comm_init(idbuf.ctypes.data_as(C.c_void_p), world, rank), "comm_init")
+
+
+def destroy_comm() -> None:
+    check(lib().fpngb_comm_destroy(), "comm_destroy")
+
+
+def comm_info():
+    n, r, p = C.c_int(), C.c_int(), C.c_int()
+    rc = lib().fpngb_comm_info(C.byref(n), C.byref(r), C.byref(p))
+    return rc == 0, n.value, r.value, bool(p.value)
+
+
+def gather_setup(window_bytes: int, max_files_per_rank: int) -> None:
+    """Collective: receive window on every rank + peer mappings (CUDA IPC over NVLink)."""
+    check(lib().fpngb_gather_setup(window_bytes, max_files_per_rank), "gather_setup")
+
+
+def gather_encoded_device(out, sizes, dst_rank: int = 0, stream=None):
+    """Collective, stream-ordered, no host synchronisation on the peer-window path.  out [n_local, stride] uint8 CUDA,
+    sizes [n_local] int32.  Returns zero-copy views (window uint8 [window_bytes], offsets int64 [nranks*nmax+1],
+    all_sizes int32 [nranks*nmax]) of library-owned device memory; meaningful on the receiving rank(s) after `stream`."""
+    import torch
+
+    ok, nranks, rank, p2p = comm_info()
+    assert ok, "init_comm() first"
+    s = stream if stream is not None else torch.cuda.current_stream(out.device).cuda_stream
+    win, offs, alls = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    n_local = int(out.shape[0])
+    check(lib().fpngb_gather_encoded_device(out.data_ptr() if n_local else None, out.stride(0) if n_local else 16,
+                                            sizes.data_ptr() if n_local else None, n_local, dst_rank,
+                                            C.byref(win), C.byref(offs), C.byref(alls), s), "gather_encoded_device")
+    return win.value, offs.value, alls.value
+
+
+def gathered_views(win_ptr: int, offs_ptr: int, sizes_ptr: int, window_bytes: int, nranks: int, nmax: int, device):
+    import torch
+
+    window = torch.as_tensor(_DevArray(win_ptr, window_bytes, "|u1", 1), device=device)
+    offsets = torch.as_tensor(_DevArray(offs_ptr, (nranks * nmax + 1) * 8, "<i8", 8), device=device)
+    all_sizes = torch.as_tensor(_DevArray(sizes_ptr, nranks * nmax * 4, "<i4", 4), device=device)
+    return window, offsets, all_sizes

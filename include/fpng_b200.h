@@ -127,6 +127,33 @@ FPNGB_API int fpngb_adler32_ex(const void* data, size_t size, uint32_t adler, ui
 FPNGB_API int fpngb_compact_batch_device(const void* d_files, size_t stride, const uint32_t* d_sizes, uint32_t n,
                                          void* d_dst, size_t dst_cap, uint64_t* d_offsets, void* stream);
 
+/* ---- multi-GPU (no reference counterpart: fpng is single-threaded, single-device) ----------------------
+ * One process per GPU.  Images shard across ranks with no collective on the data path; afterwards ONE gather brings the
+ * encoded files of every rank to the collecting rank (or to every rank).  The communicator is an NCCL communicator on the
+ * device given to fpngb_init(): either created here from a ncclUniqueId the caller distributes out of band
+ * (fpngb_comm_unique_id on one rank -> any broadcast -> fpngb_comm_init on every rank; collective), or adopted from the
+ * caller (fpngb_comm_adopt(ncclComm_t)).
+ * fpngb_gather_setup (collective): allocates a receive window of window_bytes on every rank and maps every peer's window
+ *   over NVLink (CUDA IPC); max_files_per_rank bounds n_local of the gathers that follow.
+ * fpngb_gather_encoded_device (collective, stream-ordered, NO host synchronisation when the peer windows are mapped):
+ *   all-gathers the file sizes, derives the packed layout on the device and has every rank store its files directly into
+ *   the receiver's window with 128-bit peer stores; a 4-byte all-reduce is the completion barrier.  dst_rank = -1 delivers
+ *   to every rank.  Outputs (device pointers owned by the library, valid until the next setup/destroy, to be consumed on
+ *   `stream`): *d_window = packed files of all ranks in rank order, each 16-byte aligned; (*d_offsets)[r*nmax + i] = byte
+ *   offset of file i of rank r, (*d_offsets)[nranks*nmax] = total bytes (bit 63 set: window too small, files that did
+ *   not fit were not copied); (*d_all_sizes)[r*nmax + i] = file size (0 for unused slots).  Without P2P/IPC the same
+ *   call falls back to grouped ncclSend/ncclRecv (one host synchronisation for the byte counts); fpngb_comm_info reports
+ *   which path is active. */
+#define FPNGB_UNIQUE_ID_BYTES 128
+FPNGB_API int fpngb_comm_unique_id(void* id128);
+FPNGB_API int fpngb_comm_init(const void* id128, int nranks, int rank);
+FPNGB_API int fpngb_comm_adopt(void* nccl_comm);
+FPNGB_API int fpngb_comm_destroy(void);
+FPNGB_API int fpngb_comm_info(int* nranks, int* rank, int* p2p);
+FPNGB_API int fpngb_gather_setup(size_t window_bytes, uint32_t max_files_per_rank);
+FPNGB_API int fpngb_gather_encoded_device(const void* d_files, size_t stride, const uint32_t* d_sizes, uint32_t n_local, int dst_rank,
+                                          void** d_window, uint64_t** d_offsets, uint32_t** d_all_sizes, void* stream);
+
 /* ---- static-table training (reference: FPNG_TRAIN_HUFFMAN_TABLES, fpng_test -t; src/fpng.h:114-120) ----
  * fpngb_train_accumulate_device: adds each image's 16-bit scaled symbol counts (what the reference accumulates in
  *   g_huff_counts, src/fpng.cpp:751-755) to counts[288] (host); the histogram runs in the 2-pass histogram kernel.
