@@ -36,8 +36,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + LINK_FLAGS
-    subprocess.check_call(cmd, cwd=CSRC)
+    # one object per source, compiled in parallel and only when the source or a header changed; then one link
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(PKG, "..", "include", "*.h"))
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            subprocess.check_call([nvcc] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src], cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    tmp = LIB + ".building"           # not *.so: a half-written library must never be picked up (or shipped to the GPU box)
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-o", tmp] + objs + LINK_FLAGS, cwd=CSRC)
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -10,13 +10,11 @@
 // the padding is undone with x^(-8*pad).  Pre/post conditioning (init/xorout 0xFFFFFFFF) is the usual
 // "invert the first four message bytes, invert the result".
 #include "kernels.cuh"
+#include "crc_math.cuh"
 #include <string.h>
 
 namespace fpngb {
 
-constexpr uint32_t kCrcPoly = 0xEDB88320u;          // reflected IEEE 802.3 (fpng.cpp:195-249)
-constexpr uint32_t kCrcOne = 0x80000000u;           // the polynomial "1" in reflected form
-constexpr uint32_t kCrcXInv = 0xDB710641u;          // x^-1 mod P = (P - 1) / x
 constexpr int kCrcThreads = 256;
 constexpr int kChunkWords = 32;                     // 128 bytes per thread
 constexpr int kTileWords = kCrcThreads * kChunkWords;
@@ -29,25 +27,6 @@ __constant__ uint32_t c_level[8];                   // x^(8 * 128 * 2^k): chunk-
 __constant__ uint32_t c_tile;                       // x^(8 * kTileBytes)
 __device__ uint32_t g_crc_tables[4][256];           // slice-by-4
 __device__ uint32_t g_crc_mul[8][8][16];            // g_crc_mul[k][j][n] = (n << 4j) * x^(8*128*2^k) mod P: multiply-by-constant as 8 nibble lookups
-
-__host__ __device__ inline uint32_t gf2_mulmod(uint32_t a, uint32_t b)
-{
-    uint32_t p = 0;
-#pragma unroll 8
-    for (int i = 0; i < 32; i++) {
-        p ^= (a & (0x80000000u >> i)) ? b : 0u;
-        b = (b >> 1) ^ ((b & 1u) ? kCrcPoly : 0u);
-    }
-    return p;
-}
-
-__device__ inline uint32_t gf2_pow(const uint32_t* tab, unsigned long long e)
-{
-    uint32_t r = kCrcOne;
-    for (int k = 0; e; k++, e >>= 1)
-        if (e & 1ull) r = gf2_mulmod(r, tab[k]);
-    return r;
-}
 
 static uint32_t h_tables[4][256];
 static bool h_tables_ready = false;
@@ -131,6 +110,7 @@ __global__ void __launch_bounds__(kCrcThreads) idat_crc_kernel(CrcParams p)
 
     const uint32_t img = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     ImageState* st = p.st + img;
+    if (p.stored_only && !st->stored) return;
     const uint32_t L = kPngHeaderSize + st->zsize;                      // end of the CRC'd region (buffer offset)
     const uint32_t start = p.msg_start, init = p.init_xor;
     const uint32_t ntiles = (L + kTileBytes - 1) / kTileBytes;

@@ -23,20 +23,72 @@
 // back to stored blocks are rewritten by the stored path of the pack kernel.
 #include "row_walk16.cuh"
 #include "kernels.cuh"
+#include "crc_math.cuh"
+#include <string.h>
 
 namespace fpngb {
+
+// ---- CRC-32 of the IDAT chunk computed while the bits are still in shared memory (fpng.cpp:1797 does a second pass over the
+// output with PCLMULQDQ folding, fpng.cpp:255-281).  The CRC is GF(2)-linear in the message BITS and Deflate packs bits
+// LSB-first exactly like the reflected CRC consumes them, so a row group's bit string contributes
+//        raw_crc(bit string, zero padded to whole words) * x^(bits between the padded end and the end of the message)
+// independent of its (sub-byte) position.  The kernel stores the raw CRC per group; fused_crc_kernel multiplies the powers.
+// Inside a group: lanes stride over the staging words (a register advanced over 32 words = 128 bytes per step: slice
+// tables g_f128b), chunks of kCrcChunkWords words per warp, aligned to the END of the group's string so that the lane and
+// chunk multipliers are constants (nibble tables in global memory, L1 resident).
+constexpr uint32_t kCrcChunkWords = 256;          // words per warp chunk: 8 lane steps
+__device__ uint32_t g_f128b[4][256];              // byte k of (reg ^ word) advanced over 128 bytes
+__device__ uint32_t g_lane_mul[32][8][16];        // nibble tables: multiply by x^(32 * (32 - lane))
+__device__ uint32_t g_chunk_mul[32][8][16];       // nibble tables: multiply by x^(32 * kCrcChunkWords * m)
+__constant__ uint32_t c_fx_pow2[64];              // x^(2^k)
+
+__device__ __forceinline__ uint32_t mul_nibbles(const uint32_t (*t)[16], uint32_t a)
+{
+    uint32_t r = __ldg(&t[0][a & 15u]);
+#pragma unroll
+    for (int j = 1; j < 8; j++) r ^= __ldg(&t[j][(a >> (4 * j)) & 15u]);
+    return r;
+}
+
+int fused_tables_init()
+{
+    static uint32_t t[4][256], f[4][256], lane[32][8][16], chunk[32][8][16], xp[64];
+    for (uint32_t n = 0; n < 256; n++) {
+        uint32_t c = n;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (kCrcPoly ^ (c >> 1)) : (c >> 1);
+        t[0][n] = c;
+    }
+    for (uint32_t n = 0; n < 256; n++) for (int k = 1; k < 4; k++) t[k][n] = (t[k - 1][n] >> 8) ^ t[0][t[k - 1][n] & 0xFF];
+    xp[0] = 0x40000000u;
+    for (int k = 1; k < 64; k++) xp[k] = gf2_mulmod(xp[k - 1], xp[k - 1]);
+    auto xpow = [&](unsigned long long e) { uint32_t r = kCrcOne; for (int k = 0; e; k++, e >>= 1) if (e & 1ull) r = gf2_mulmod(r, xp[k]); return r; };
+    // the word update "reg = T3[b0] ^ T2[b1] ^ T1[b2] ^ T0[b3]" advances (reg ^ word) over 4 bytes; 124 more bytes = x^(8*124)
+    const uint32_t adv = xpow(8ull * 124ull);
+    for (int k = 0; k < 4; k++) for (uint32_t n = 0; n < 256; n++) f[k][n] = gf2_mulmod(t[3 - k][n], adv);
+    for (uint32_t l = 0; l < 32; l++) { const uint32_t c = xpow(32ull * (32 - l)); for (int j = 0; j < 8; j++) for (uint32_t n = 0; n < 16; n++) lane[l][j][n] = gf2_mulmod(n << (4 * j), c); }
+    for (uint32_t m = 0; m < 32; m++) { const uint32_t c = xpow(32ull * kCrcChunkWords * m); for (int j = 0; j < 8; j++) for (uint32_t n = 0; n < 16; n++) chunk[m][j][n] = gf2_mulmod(n << (4 * j), c); }
+    FPNGB_CUDA_OK(cudaMemcpyToSymbol(g_f128b, f, sizeof f));
+    FPNGB_CUDA_OK(cudaMemcpyToSymbol(g_lane_mul, lane, sizeof lane));
+    FPNGB_CUDA_OK(cudaMemcpyToSymbol(g_chunk_mul, chunk, sizeof chunk));
+    FPNGB_CUDA_OK(cudaMemcpyToSymbol(c_fx_pow2, xp, sizeof xp));
+    return 0;
+}
 
 constexpr int kFusedWarps = 8;                    // units per row group (upper bound)
 constexpr uint32_t kStateAgg = 1ull, kStateIncl = 2ull;
 constexpr unsigned long long kValueMask = (1ull << 62) - 1ull;
 constexpr unsigned long long kTailReady = 1ull << 63;
-constexpr uint32_t kSpinLimit = 1u << 27;         // a bug must fail the run, never hang the GPU
+constexpr uint32_t kSpinLimit = 1u << 22;         // a bug must fail the run, never hang the GPU
 
 template <int CHANS> __host__ __device__ constexpr int fused_slot_words() { return CHANS == 3 ? 21 : 27; }   // lane-local bit string (odd: conflict-free)
 template <int CHANS> __host__ __device__ constexpr int fused_unit_words() { return (512 * 12 * CHANS + 18 + 12 + 12) / 32 + 2; }   // staging words per unit, worst case
-template <int CHANS> __host__ __device__ constexpr int fused_unit_bytes()
+// scanline loader of the kernel: staged tiles (TMA / cp.async) for 16-byte aligned scanlines, direct realigning loads otherwise
+template <int CHANS, bool DIRECT> struct FusedLoader { using type = Walk16<CHANS>; };
+template <int CHANS> struct FusedLoader<CHANS, true> { using type = Walk16Direct<CHANS>; };
+template <int CHANS, bool DIRECT> __host__ __device__ constexpr int fused_unit_bytes()
 {
-    return Walk16<CHANS>::kWarpBytes > 32 * fused_slot_words<CHANS>() * 4 ? Walk16<CHANS>::kWarpBytes : 32 * fused_slot_words<CHANS>() * 4;
+    using WK = typename FusedLoader<CHANS, DIRECT>::type;
+    return WK::kWarpBytes > 32 * fused_slot_words<CHANS>() * 4 ? WK::kWarpBytes : 32 * fused_slot_words<CHANS>() * 4;
 }
 
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" :: "r"(saddr), "r"(v) : "memory"); }
@@ -111,7 +163,8 @@ __device__ __forceinline__ uint32_t frun_before(uint32_t eqm, uint32_t r_in, uin
 struct GroupDesc {                                // 32 bytes per row group; zeroed before every launch
     unsigned long long agg;                       // [63:62] 0 empty / 1 aggregate / 2 inclusive, [61:0] bits (aggregate) or end bit position (inclusive)
     unsigned long long tail;                      // bit 63 ready; low 32 bits: the partial word this group shares with its successor
-    unsigned long long pad_[2];
+    unsigned long long crc;                       // low 32 bits: raw CRC of the group's bit string zero-padded to whole words; high 32: those words
+    unsigned long long pad_;
 };
 
 struct FusedParams {
@@ -122,14 +175,16 @@ struct FusedParams {
     uint32_t rows_per_group, steps_per_row, groups_per_image, n_images;
     uint8_t* out; size_t out_stride;
     uint32_t merge_first_unit;
+    uint32_t inline_crc;
 };
 
-template <int CHANS>
+template <int CHANS, bool DIRECT>
 __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_fused_kernel(FusedParams p)
 {
+    using WK = typename FusedLoader<CHANS, DIRECT>::type;
     constexpr uint32_t M = max_match_pixels(CHANS);
     constexpr int kHalfWords = 2 * CHANS;
-    constexpr int kUnitBytes = fused_unit_bytes<CHANS>();
+    constexpr int kUnitBytes = fused_unit_bytes<CHANS, DIRECT>();
     constexpr int kSlotWords = fused_slot_words<CHANS>();
     constexpr int kUnitWords = fused_unit_words<CHANS>();
     extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -139,9 +194,9 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
     const uint32_t stage_words = kFusedWarps * kUnitWords + 2;
     uint32_t* s_lit = s_stage + stage_words;
     uint32_t* s_match = s_lit + 512;
-    uint32_t* s_small = s_match + 88;
+    uint32_t* s_small = s_match + 88;               // 48 words
     // s_small: [0..7] has_lit, [8..15] trail, [16..23] npix, [24..31] unit bits, [32] ticket, [33] pred tail, [34] sh, [35] status
-    unsigned long long* s_u64 = reinterpret_cast<unsigned long long*>(s_small + 40);     // [0..7] adler A, [8..15] adler B, [16] base (file bit of the group's first bit)
+    unsigned long long* s_u64 = reinterpret_cast<unsigned long long*>(s_small + 48);     // [0..7] adler A, [8..15] adler B, [16] base (file bit of the group's first bit)
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
     if (tid == 0) s_small[32] = atomicAdd(p.ticket, 1u);
@@ -153,6 +208,8 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
     const CodeBook* book = p.books + (size_t)img * p.book_stride;
     for (uint32_t i = tid; i < 256; i += blockDim.x) { s_lit[i] = book->lit[i]; s_lit[256 + i] = 0u; }
     if (tid < 88) s_match[tid] = book->match[tid];
+    uint32_t* s_crc = reinterpret_cast<uint32_t*>(s_u64 + 18);                // [4][256] slice tables of the 128-byte advance
+    if (p.inline_crc) for (uint32_t i = tid; i < 1024; i += blockDim.x) s_crc[i] = (&g_f128b[0][0])[i];
 
     const uint32_t w = p.w, bpl = w * CHANS, S = p.steps_per_row;
     const uint32_t r_in_group = warp / S, step = warp - r_in_group * S;
@@ -162,7 +219,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
     const uint32_t lit_s = smem_u32(s_lit), match_s = smem_u32(s_match);
 
     // ---- phase 1: load, filter, Adler, equality
-    uint32_t dw[Walk16<CHANS>::kWords];
+    uint32_t dw[WK::kWords];
     uint32_t eqm = 0, litm = 0, nvp = 0, trail = 0, has_lit_ballot = 0;
     bool last = false;
     uint32_t sumA = 0; unsigned long long sumB = 0;
@@ -171,7 +228,8 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
     if (active) {
         cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
         prev = y ? cur - bpl : nullptr;
-        Walk16<CHANS> wk; wk.init(lane, unit_mem);
+        WK wk; wk.init(lane, unit_mem);
+        wk.bind(cur, prev);
         wk.prefetch(cur, prev, step, bpl, lane, unit_mem);
         // the filtered pixel left of this unit (lane 0 only needs it): a few byte loads that overlap the tile copy
         uint32_t left_px = 0;
@@ -185,7 +243,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
         }
         wk.template consume<true>(prev != nullptr, 0u, step, bpl, lane, unit_mem, dw, sumA, sumB);
         uint32_t px[16];
-        Walk16<CHANS>::pixels(dw, px);
+        WK::pixels(dw, px);
         nvp = p0 < w ? min(16u, w - p0) : 0u;
         uint32_t left = __shfl_up_sync(kFullMask, px[15], 1);
         if (lane == 0) left = left_px;
@@ -313,7 +371,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
                 uint32_t lu;
                 if (litm & (1u << k)) {
                     uint32_t px[16];
-                    Walk16<CHANS>::pixels(dw, px);
+                    WK::pixels(dw, px);
                     uint32_t lastpx = px[0];
 #pragma unroll
                     for (int q = 1; q < 16; q++) lastpx = (k == (uint32_t)q) ? px[q] : lastpx;
@@ -337,6 +395,8 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
 
     GroupDesc* desc = p.desc + (size_t)img * p.groups_per_image;
     if (warp == 0) {
+        // publish this group's bit count at once: later groups can already sum it while this one is still busy
+        if (g != 0 && lane == 0) st_volatile_u64(&desc[g].agg, ((unsigned long long)kStateAgg << 62) | group_bits);
         // Adler-32 partials per scanline (rows of this group; their units are this CTA's warps)
         if (lane < p.rows_per_group && g * p.rows_per_group + lane < p.h) {
             unsigned long long A = 0, B = 0;
@@ -344,41 +404,6 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
             const uint32_t yy = g * p.rows_per_group + lane, filt = yy ? 2u : 0u;
             const unsigned long long n = (unsigned long long)bpl + 1ull, S1 = A + filt, S2 = n * S1 - (A + B);
             p.row_adler[(size_t)img * p.h + yy] = make_uint2((uint32_t)(S1 % kAdlerMod), (uint32_t)(S2 % kAdlerMod));
-        }
-        // decoupled look-back (single-pass chained scan): publish the aggregate, sum the aggregates of the groups before,
-        // stop at the first group that already knows its inclusive end position
-        unsigned long long base = 0;
-        uint32_t status = 0;
-        if (g == 0) {
-            base = (unsigned long long)kZlibBitBase + book->hdr_bits;
-        } else {
-            if (lane == 0) st_volatile_u64(&desc[g].agg, ((unsigned long long)kStateAgg << 62) | group_bits);
-            int j = (int)g - 1;
-            bool done = false;
-            uint32_t spins = 0;
-            while (!done) {
-                const int idx = j - (int)lane;
-                unsigned long long v = idx >= 0 ? ld_volatile_u64(&desc[idx].agg) : ((unsigned long long)kStateIncl << 62);   // before group 0: nothing
-                const uint32_t state = (uint32_t)(v >> 62);
-                if (__any_sync(kFullMask, state == 0u)) {                    // some predecessor has not published yet: look again
-                    if (++spins > kSpinLimit) { status = 1u; break; }
-                    continue;
-                }
-                const uint32_t incl = __ballot_sync(kFullMask, state == kStateIncl);
-                const uint32_t first = incl ? (uint32_t)__ffs((int)incl) - 1u : 32u;       // nearest group with an inclusive value
-                unsigned long long contrib = (lane <= first && idx >= 0) ? (v & kValueMask) : 0ull;
-                contrib = warp_sum_u64(contrib);
-                base += contrib;
-                if (incl) done = true; else j -= 32;
-            }
-            // (lanes with idx < 0 report "inclusive 0" only to keep the ballot well defined: group 0 always publishes an
-            //  inclusive value, so every chain ends at or before it)
-        }
-        const unsigned long long end = base + group_bits;
-        if (lane == 0) {
-            st_volatile_u64(&desc[g].agg, ((unsigned long long)kStateIncl << 62) | end);
-            s_u64[16] = base;
-            s_small[35] = status;
         }
     }
 
@@ -397,6 +422,44 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
             else if (outw) red_or32(stage_s + k * 4u, outw);
         }
     }
+    if (warp == 0) {
+        // decoupled look-back (single-pass chained scan), after this warp's own copy so that the wait overlaps useful work:
+        // sum the aggregates of the groups before, stop at the first group that already knows its inclusive end position
+        unsigned long long base = 0;
+        uint32_t status = 0;
+        if (g == 0) {
+            base = (unsigned long long)kZlibBitBase + book->hdr_bits;
+        } else {
+            int j = (int)g - 1;
+            bool done = false;
+            uint32_t spins = 0;
+            while (!done) {
+                const int idx = j - (int)lane;
+                unsigned long long v = idx >= 0 ? ld_volatile_u64(&desc[idx].agg) : ((unsigned long long)kStateIncl << 62);   // before group 0: nothing
+                const uint32_t state = (uint32_t)(v >> 62);
+                const uint32_t incl = __ballot_sync(kFullMask, state == kStateIncl);
+                const uint32_t empty = __ballot_sync(kFullMask, state == 0u);
+                const uint32_t first = incl ? (uint32_t)__ffs((int)incl) - 1u : 32u;       // nearest group with an inclusive value
+                const uint32_t needed = first >= 31u ? kFullMask : ((2u << first) - 1u);   // lanes whose value enters the sum
+                if (empty & needed) {                                       // a predecessor that matters has not published yet: look again
+                    if (++spins > kSpinLimit) { status = 1u; break; }
+                    continue;
+                }
+                unsigned long long contrib = (lane <= first && idx >= 0) ? (v & kValueMask) : 0ull;
+                contrib = warp_sum_u64(contrib);
+                base += contrib;
+                if (incl) done = true; else j -= 32;
+            }
+            // (lanes with idx < 0 report "inclusive 0" only to keep the ballot well defined: group 0 always publishes an
+            //  inclusive value, so every chain ends at or before it)
+        }
+        const unsigned long long end = base + group_bits;
+        if (lane == 0) {
+            st_volatile_u64(&desc[g].agg, ((unsigned long long)kStateIncl << 62) | end);
+            s_u64[16] = base;
+            s_small[35] = status;
+        }
+    }
     __syncthreads();                                                         // #3: staging complete, base known
     const unsigned long long base = s_u64[16];
     const uint32_t sh = (uint32_t)(base & 31ull);
@@ -404,8 +467,41 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
     const uint32_t span = sh + group_bits, nfull = span >> 5;                // words whose bit 31 this group covers
     if (s_small[35]) { if (tid == 0) p.st[img].status = 2u; return; }
 
+    // ---- CRC-32 partial of the group's bit string (staging words, group-relative: independent of the file position)
+    if (p.inline_crc) {
+        const uint32_t NW = (group_bits + 31u) >> 5;
+        uint32_t acc = 0;
+        // warp `warp` takes the chunks warp, warp + nwarps, ... counted from the END of the string
+        for (uint32_t m = warp; m * kCrcChunkWords < NW; m += nwarps) {
+            const int j0 = (int)NW - (int)((m + 1u) * kCrcChunkWords) + (int)lane;      // this lane's first word of the chunk (may be < 0: front padding)
+            uint32_t c = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < kCrcChunkWords / 32u; k++) {
+                const int j = j0 + (int)(32u * k);
+                const uint32_t x = c ^ (j >= 0 ? s_stage[j] : 0u);
+                if (k + 1u < kCrcChunkWords / 32u)
+                    c = s_crc[x & 0xFFu] ^ s_crc[256 + ((x >> 8) & 0xFFu)] ^ s_crc[512 + ((x >> 16) & 0xFFu)] ^ s_crc[768 + (x >> 24)];
+                else c = x;
+            }
+            c = mul_nibbles(g_lane_mul[lane], c);                              // lane l's last word sits 31 - l words before the chunk end
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(kFullMask, c, o);
+            // position the chunk: m chunks follow it (lanes 0..7 look up one nibble each)
+            uint32_t part = lane < 8u ? __ldg(&g_chunk_mul[m & 31u][lane][(c >> (4u * lane)) & 15u]) : 0u;
+            part ^= __shfl_xor_sync(kFullMask, part, 4); part ^= __shfl_xor_sync(kFullMask, part, 2); part ^= __shfl_xor_sync(kFullMask, part, 1);
+            acc ^= part;
+        }
+        if (lane == 0) s_small[36 + warp] = acc;
+    }
+
     // ---- phase 4b: the word shared with the predecessor / successor
     if (tid == 0) {
+        // this group's own trailing partial word (bits below span & 31 of word nfull).  When the group completes at least
+        // one word (nfull >= 1: always, except for degenerate tiny groups) the tail does not depend on the predecessor and is
+        // published BEFORE waiting for the predecessor's, so the tails of consecutive groups do not form a serial chain.
+        uint32_t tailw = 0;
+        if (span & 31u) tailw = __funnelshift_l(nfull ? s_stage[nfull - 1] : 0u, s_stage[nfull], sh);
+        if (nfull) st_volatile_u64(&desc[g].tail, kTailReady | tailw);
         uint32_t pred = 0;
         if (sh) {
             if (g == 0) {
@@ -421,16 +517,14 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
             }
         }
         s_small[33] = pred;
-        // this group's own trailing partial word (bits below span & 31 of word nfull)
-        uint32_t tailw = 0;
-        if (span & 31u) {
-            const uint32_t lo = nfull ? s_stage[nfull - 1] : 0u;
-            tailw = __funnelshift_l(lo, s_stage[nfull], sh);
-            if (nfull == 0) tailw |= pred;
-        }
-        st_volatile_u64(&desc[g].tail, kTailReady | tailw);
+        if (!nfull) st_volatile_u64(&desc[g].tail, kTailReady | tailw | pred);
     }
-    __syncthreads();                                                         // #4: pred tail
+    __syncthreads();                                                         // #4: pred tail, CRC partials
+    if (p.inline_crc && tid == 0) {
+        uint32_t r = 0;
+        for (uint32_t u = 0; u < nwarps; u++) r ^= s_small[36 + u];
+        desc[g].crc = (unsigned long long)r | ((unsigned long long)((group_bits + 31u) >> 5) << 32);
+    }
     // ---- phase 4c: write the complete words, shifted to the group's position in the file
     {
         uint32_t* gw = reinterpret_cast<uint32_t*>(p.out + (size_t)img * p.out_stride);
@@ -519,16 +613,83 @@ __global__ void __launch_bounds__(256) fused_finish_kernel(FinishParams p)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// CRC-32 of "IDAT" + zlib stream (fpng.cpp:1797-1800) from the per-group partials, one CTA per image.  With E = end of the
+// message (file bit (58 + zsize) * 8), a piece that starts at file bit s and whose raw CRC covers nw words contributes
+// raw * x^(E - s - 32 nw).  Pieces: the bytes/bits before the first token ("IDAT", zlib header, block header), the row
+// groups, the four Adler-32 bytes.  Initial value and final XOR (0xFFFFFFFF) are applied by linearity.
+// ------------------------------------------------------------------------------------------------------------------
+struct FusedCrcParams {
+    const GroupDesc* desc; uint32_t groups_per_image;
+    const CodeBook* books; uint32_t book_stride;
+    const ImageState* st;
+    uint8_t* out; size_t out_stride;
+};
+
+__device__ __forceinline__ uint32_t crc_bit_step(uint32_t reg, uint32_t bit) { return (reg >> 1) ^ (((reg ^ bit) & 1u) ? kCrcPoly : 0u); }
+
+__global__ void __launch_bounds__(256) fused_crc_kernel(FusedCrcParams p)
+{
+    __shared__ uint32_t s_part[8];
+    const uint32_t img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ImageState st = p.st[img];
+    if (st.stored || st.status) return;                                      // stored-block images: idat_crc_kernel reads the file
+    const CodeBook* book = p.books + (size_t)img * p.book_stride;
+    const GroupDesc* desc = p.desc + (size_t)img * p.groups_per_image;
+    const unsigned long long E = (unsigned long long)(kPngHeaderSize + st.zsize) * 8ull;
+    const unsigned long long msg0 = (unsigned long long)(kPngHeaderSize - 4u) * 8ull, base0 = (unsigned long long)kZlibBitBase + book->hdr_bits;
+    uint32_t acc = 0;
+    for (uint32_t g = tid; g < p.groups_per_image; g += blockDim.x) {
+        const unsigned long long c = desc[g].crc;
+        const unsigned long long start = g ? (desc[g - 1].agg & kValueMask) : base0;
+        const unsigned long long e = E - start - 32ull * (c >> 32);
+        acc ^= gf2_mulmod((uint32_t)c, gf2_pow(c_fx_pow2, e));
+    }
+    if (tid == 0) {
+        // "IDAT" + header bits, bit by bit (a few hundred to ~2400 bits), then shifted to the end of the message
+        uint32_t reg = 0;
+        const uint8_t tag[4] = {'I', 'D', 'A', 'T'};
+        for (int i = 0; i < 32; i++) reg = crc_bit_step(reg, (tag[i >> 3] >> (i & 7)) & 1u);
+        const uint32_t hb = book->hdr_bits;
+        for (uint32_t i = 0; i < hb; i++) reg = crc_bit_step(reg, (book->hdr[i >> 3] >> (i & 7)) & 1u);
+        acc ^= gf2_mulmod(reg, gf2_pow(c_fx_pow2, E - base0));
+        // Adler-32, big-endian, last four bytes of the message
+        uint32_t ra = 0;
+        for (int i = 0; i < 32; i++) { const uint32_t byte = (st.adler >> (24 - 8 * (i >> 3))) & 0xFFu; ra = crc_bit_step(ra, (byte >> (i & 7)) & 1u); }
+        acc ^= ra;
+        // initial register value 0xFFFFFFFF advanced over the whole message, and the final XOR
+        acc ^= gf2_mulmod(0xFFFFFFFFu, gf2_pow(c_fx_pow2, E - msg0)) ^ 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t crc = 0;
+        for (int i = 0; i < 8; i++) crc ^= s_part[i];
+        uint8_t* q = p.out + (size_t)img * p.out_stride + kPngHeaderSize + st.zsize;
+        q[0] = (uint8_t)(crc >> 24); q[1] = (uint8_t)(crc >> 16); q[2] = (uint8_t)(crc >> 8); q[3] = (uint8_t)crc;
+    }
+}
+
+void launch_fused_crc(const void* desc_mem, uint32_t n, uint32_t w, uint32_t h, const CodeBook* books, uint32_t book_stride, const ImageState* st,
+                      uint8_t* out, size_t out_stride, cudaStream_t s)
+{
+    const uint32_t S = (w + kStep16 - 1) / kStep16, R = kFusedWarps / S, G = (h + R - 1) / R;
+    FusedCrcParams c{(const GroupDesc*)desc_mem, G, books, book_stride, st, out, out_stride};
+    fused_crc_kernel<<<n, 256, 0, s>>>(c);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-template <int CHANS> constexpr size_t fused_smem()
+template <int CHANS, bool DIRECT> constexpr size_t fused_smem()
 {
-    return (size_t)kFusedWarps * fused_unit_bytes<CHANS>() + ((size_t)kFusedWarps * fused_unit_words<CHANS>() + 2 + 512 + 88 + 40) * 4 + 17 * 8 + 16;
+    return (size_t)kFusedWarps * fused_unit_bytes<CHANS, DIRECT>() + ((size_t)kFusedWarps * fused_unit_words<CHANS>() + 2 + 512 + 88 + 48) * 4 + 18 * 8 + 1024 * 4 + 16;
 }
 
 bool fused_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t h, uint32_t chans, uint32_t n)
 {
-    if (!walk16_eligible(base, image_stride, w, chans)) return false;
+    (void)base; (void)image_stride; (void)chans;             // any alignment: unaligned scanlines use the direct loader
     const uint32_t S = (w + kStep16 - 1) / kStep16;
     if (S > (uint32_t)kFusedWarps) return false;
     const uint32_t R = kFusedWarps / S;
@@ -546,7 +707,7 @@ size_t fused_desc_bytes(uint32_t n, uint32_t w, uint32_t h)
 int launch_encode_fused(const uint8_t* pixels, size_t image_stride, uint32_t n, uint32_t w, uint32_t h, uint32_t chans, uint32_t flags,
                         const CodeBook* books, uint32_t book_stride, uint2* row_adler, ImageState* st, void* desc_mem,
                         uint8_t* out, size_t out_stride, uint32_t* sizes, const uint8_t* png_header, uint32_t merge_first_unit, cudaStream_t s,
-                        cudaEvent_t mid_event)
+                        cudaEvent_t mid_event, bool inline_crc)
 {
     const uint32_t S = (w + kStep16 - 1) / kStep16, R = kFusedWarps / S, G = (h + R - 1) / R;
     const size_t dbytes = (size_t)n * G * sizeof(GroupDesc);
@@ -556,16 +717,15 @@ int launch_encode_fused(const uint8_t* pixels, size_t image_stride, uint32_t n, 
     p.pixels = pixels; p.image_stride = image_stride; p.w = w; p.h = h; p.books = books; p.book_stride = book_stride;
     p.row_adler = row_adler; p.st = st; p.desc = (GroupDesc*)desc_mem; p.ticket = (uint32_t*)((uint8_t*)desc_mem + dbytes);
     p.rows_per_group = R; p.steps_per_row = S; p.groups_per_image = G; p.n_images = n; p.out = out; p.out_stride = out_stride;
-    p.merge_first_unit = merge_first_unit;
+    p.merge_first_unit = merge_first_unit; p.inline_crc = inline_crc ? 1u : 0u;
     const uint32_t threads = 32u * R * S;
     const unsigned long long groups = (unsigned long long)n * G;
-    if (chans == 4) {
-        FPNGB_SET_SMEM(encode_fused_kernel<4>, fused_smem<4>());
-        encode_fused_kernel<4><<<(uint32_t)groups, threads, fused_smem<4>(), s>>>(p);
-    } else {
-        FPNGB_SET_SMEM(encode_fused_kernel<3>, fused_smem<3>());
-        encode_fused_kernel<3><<<(uint32_t)groups, threads, fused_smem<3>(), s>>>(p);
-    }
+    const bool direct = !walk16_eligible(pixels, image_stride, w, chans);
+#define FPNGB_LAUNCH_FUSED(C, D) do { FPNGB_SET_SMEM((encode_fused_kernel<C, D>), (fused_smem<C, D>())); \
+        encode_fused_kernel<C, D><<<(uint32_t)groups, threads, fused_smem<C, D>(), s>>>(p); } while (0)
+    if (chans == 4) { if (direct) FPNGB_LAUNCH_FUSED(4, true); else FPNGB_LAUNCH_FUSED(4, false); }
+    else { if (direct) FPNGB_LAUNCH_FUSED(3, true); else FPNGB_LAUNCH_FUSED(3, false); }
+#undef FPNGB_LAUNCH_FUSED
     if (mid_event) cudaEventRecord(mid_event, s);                            // profiling: end of the fused kernel
     FinishParams f{};
     f.desc = (const GroupDesc*)desc_mem; f.groups_per_image = G; f.books = books; f.book_stride = book_stride; f.st = st;

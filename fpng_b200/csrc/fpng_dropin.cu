@@ -10,6 +10,13 @@
 
 #define DROPIN_API __attribute__((visibility("default")))
 
+static fpngb_fallback_decoder g_fallback = nullptr;
+static void* g_fallback_user = nullptr;
+extern "C" {
+void fpngb_set_fallback_decoder(fpngb_fallback_decoder fn, void* user) { g_fallback = fn; g_fallback_user = user; }
+fpngb_fallback_decoder fpngb_get_fallback_decoder(void** user) { if (user) *user = g_fallback_user; return g_fallback; }
+}
+
 namespace fpng
 {
     DROPIN_API void fpng_init()
@@ -53,6 +60,19 @@ namespace fpng
         return fpngb_get_info(pImage, image_size, &width, &height, &channels_in_file);
     }
 
+    // a registered general-PNG decoder takes over the files fpng rejects (fpngb_set_fallback_decoder, include/fpng_b200.h)
+    static int try_fallback(const void* pImage, uint32_t image_size, std::vector<uint8_t>& out, uint32_t& width, uint32_t& height,
+                            uint32_t& channels_in_file, uint32_t desired_channels)
+    {
+        if (!g_fallback) { out.resize(0); return FPNG_DECODE_NOT_FPNG; }
+        void* px = nullptr; uint32_t w = 0, h = 0, c = 0;
+        if (g_fallback(pImage, image_size, desired_channels, g_fallback_user, &px, &w, &h, &c) != 0 || !px) { out.resize(0); return FPNG_DECODE_NOT_FPNG; }
+        out.assign((const uint8_t*)px, (const uint8_t*)px + (size_t)w * h * desired_channels);
+        free(px);
+        width = w; height = h; channels_in_file = c;
+        return FPNG_DECODE_SUCCESS;
+    }
+
     DROPIN_API int fpng_decode_memory(const void* pImage, uint32_t image_size, std::vector<uint8_t>& out, uint32_t& width, uint32_t& height,
                                       uint32_t& channels_in_file, uint32_t desired_channels)
     {
@@ -60,11 +80,13 @@ namespace fpng
         width = height = channels_in_file = 0;
         if (!pImage || !image_size || (desired_channels != 3 && desired_channels != 4)) return FPNG_DECODE_INVALID_ARG;
         int st = fpngb_get_info(pImage, image_size, &width, &height, &channels_in_file);
+        if (st == FPNG_DECODE_NOT_FPNG) return try_fallback(pImage, image_size, out, width, height, channels_in_file, desired_channels);
         if (st) return st;
         const uint64_t need = (uint64_t)width * height * desired_channels;
         if (need > 0xFFFFFFFFull) return FPNG_DECODE_FAILED_DIMENSIONS_TOO_LARGE;
         out.resize((size_t)need);
         st = fpngb_decode_host(pImage, image_size, out.data(), out.size(), &width, &height, &channels_in_file, desired_channels);
+        if (st == FPNG_DECODE_NOT_FPNG) return try_fallback(pImage, image_size, out, width, height, channels_in_file, desired_channels);
         return st;
     }
 

@@ -22,7 +22,8 @@
 namespace fpngb {
 
 static std::atomic<uint64_t> g_launches{0};
-static bool g_no_fused_override = false;       // fpngb_debug_disable_fused(): tests run both encoders in one process
+static bool g_no_fused_override = false;
+static bool g_inline_crc = true;                // fpngb_debug_inline_crc(): the single-pass encoder computes the IDAT CRC from in-kernel partials       // fpngb_debug_disable_fused(): tests run both encoders in one process
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -255,7 +256,8 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     const uint32_t lit1_rule = (!two_pass && chans == 4 && c.h_static_books[1].lit1_rule) ? 1u : 0u;
     const bool v2 = !force_generic && !lit1_rule && walk16_eligible(d_pixels, image_stride, w, chans);
     // third generation: single pass over the pixels (encode_fused.cu) for every shape it covers (w <= 4096, aligned scanlines)
-    const bool fused = v2 && !no_fused && !g_no_fused_override && !(flags & FPNGB_FORCE_UNCOMPRESSED) && fused_eligible(d_pixels, image_stride, w, h, chans, n);
+    const bool fused = !force_generic && !lit1_rule && !no_fused && !g_no_fused_override && !(flags & FPNGB_FORCE_UNCOMPRESSED) &&
+                       fused_eligible(d_pixels, image_stride, w, h, chans, n);
     Workspace ws;
     int rc = carve_workspace(c, n, h, w, two_pass, ws, fused);
     if (rc) return rc;
@@ -292,7 +294,7 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
         make_png_header(png_header, w, h, chans);
         cudaEvent_t mid = ps ? ps->ev[kProfFused + 1] : nullptr;
         rc = launch_encode_fused(d_pixels, image_stride, n, w, h, chans, flags, books, book_stride, ws.row_adler, ws.st, ws.fused_desc,
-                                 d_out, out_stride, d_sizes, png_header, sp.merge_first_unit, s, mid);
+                                 d_out, out_stride, d_sizes, png_header, sp.merge_first_unit, s, mid, g_inline_crc);
         if (rc) return rc;
         if (ps) ps->used[kProfFused] = true;
         prof_mark(ps, kProfFinish, s);
@@ -323,6 +325,11 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     CrcParams cp{};
     cp.out = d_out; cp.out_stride = out_stride; cp.st = ws.st;
     cp.max_tiles = crc_ctas_for(max_encoded_size(w, h, chans)); cp.msg_start = kPngHeaderSize - 4; cp.init_xor = 0xFFFFFFFFu;
+    if (fused && g_inline_crc) {
+        launch_fused_crc(ws.fused_desc, n, w, h, books, book_stride, ws.st, d_out, out_stride, s);   // combine the in-kernel partials
+        cp.stored_only = 1u;                                                // the file-reading CRC kernel is only needed for stored-block images
+        count_launch(1);
+    }
     launch_crc(cp, n, s);
     prof_mark(ps, kProfCrc, s);
     count_launch(4);
@@ -357,6 +364,8 @@ int fpngb_init(int device)
     FPNGB_CUDA_OK(cudaMemcpy(c.d_static_books, c.h_static_books, 2 * sizeof(CodeBook), cudaMemcpyHostToDevice));
     int rc = checksum_tables_init();
     if (rc) return rc;
+    rc = fused_tables_init();
+    if (rc) return rc;
     c.pin_small.pinned = true;
     rc = c.pin_small.reserve(1 << 16);
     if (rc) return rc;
@@ -375,6 +384,7 @@ FPNGB_API void fpngb_debug_rows_per_warp(uint32_t v) { set_rows_per_warp16(v); }
 
 // test hook: 1 = use the two-kernel (scan + pack) encoder even where the single-pass encoder applies; not part of the reference surface
 FPNGB_API void fpngb_debug_disable_fused(int off) { g_no_fused_override = off != 0; }
+FPNGB_API void fpngb_debug_inline_crc(int on) { g_inline_crc = on != 0; }
 
 // exposes the static code books to the tests (sizes[288], codes[288]); not part of the reference surface
 FPNGB_API int fpngb_debug_static_table(uint32_t chans, uint8_t* sizes, uint16_t* codes, uint32_t* hdr_bits)

@@ -58,6 +58,7 @@ struct CrcParams {
     uint32_t max_tiles;                           // grid.x; CTAs beyond an image's length exit immediately
     uint32_t msg_start;                           // first byte of the CRC'd region (54 = "IDAT" for a PNG file)
     uint32_t init_xor;                            // initial register value (0xFFFFFFFF for a fresh CRC)
+    uint32_t stored_only;                         // only images that fell back to stored blocks (the single-pass encoder computed the others' CRC inline)
 };
 
 struct HuffParams {
@@ -77,7 +78,10 @@ size_t fused_desc_bytes(uint32_t n, uint32_t w, uint32_t h);
 int launch_encode_fused(const uint8_t* pixels, size_t image_stride, uint32_t n, uint32_t w, uint32_t h, uint32_t chans, uint32_t flags,
                         const CodeBook* books, uint32_t book_stride, uint2* row_adler, ImageState* st, void* desc_mem,
                         uint8_t* out, size_t out_stride, uint32_t* sizes, const uint8_t* png_header, uint32_t merge_first_unit, cudaStream_t s,
-                        cudaEvent_t mid_event);
+                        cudaEvent_t mid_event, bool inline_crc);
+void launch_fused_crc(const void* desc_mem, uint32_t n, uint32_t w, uint32_t h, const CodeBook* books, uint32_t book_stride, const ImageState* st,
+                      uint8_t* out, size_t out_stride, cudaStream_t s);
+int fused_tables_init();
 
 void launch_scan(const ScanParams& p, uint32_t n, uint32_t chans, int mode, bool hist, cudaStream_t s);
 bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t chans);

@@ -67,6 +67,7 @@ struct Walk16Tma {
         if (lane == 0) mbar_init(warp_tiles + kMbarOfs, 1);
         __syncwarp();
     }
+    __device__ __forceinline__ void bind(const uint8_t*, const uint8_t*) {}
 
     // issue the bulk copies of one step (lane 0 only) into this warp's tile
     __device__ __forceinline__ void prefetch(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev, uint32_t step, uint32_t bpl,
@@ -153,6 +154,7 @@ struct Walk16Padded {
     static constexpr int kPadTile = 32 * kTileLaneBytes;
     static constexpr int kWarpBytes = 2 * kPadTile;           // shared memory per warp
     uint32_t soff[CHANS];                        // byte offsets inside a tile where this lane's copies land
+    __device__ __forceinline__ void bind(const uint8_t*, const uint8_t*) {}
 
     __device__ __forceinline__ void init(uint32_t lane, uint8_t*)
     {
@@ -208,6 +210,100 @@ struct Walk16Padded {
 #pragma unroll
         for (int k = 0; k < 16; k++) px[k] = dw[k];
     }
+};
+
+// ---- direct loads for scanlines of ANY alignment / width --------------------------------------------------------------
+// Real-world widths (687 x 3 = 2061-byte scanlines) give rows that start at arbitrary byte addresses, which neither TMA bulk
+// copies nor cp.async (16-byte granules) can stage.  Here every lane loads the aligned 16-byte chunks that cover its own 16
+// pixels (48 / 64 bytes: 4 or 5 LDG.128) and realigns them in registers with funnel shifts.  The lane stride is a multiple
+// of 16 bytes, so the misalignment (address & 15) is the same for every lane of the warp: the word part of the shift is a
+// warp-uniform switch, the byte part one SHF per word.  Bytes at or beyond the end of the scanline read as zero and chunks
+// that lie completely outside the lane's byte range are not loaded (nothing is read beyond the 16-byte chunk that holds the
+// scanline's last byte).
+template <int CHANS>
+struct Walk16Direct {
+    static constexpr int kWords = 4 * CHANS;
+    static constexpr int kWarpBytes = 0;                      // no staging buffer
+    __device__ __forceinline__ void init(uint32_t, uint8_t*) {}
+    __device__ __forceinline__ void prefetch(const uint8_t*, const uint8_t*, uint32_t, uint32_t, uint32_t, uint8_t*) const {}
+
+    __device__ __forceinline__ static void load_lane(const uint8_t* __restrict__ ptr, uint32_t nbytes, uint32_t (&out)[kWords])
+    {
+        constexpr int kChunks = CHANS + 1;                    // 16-byte chunks that can overlap the lane's 16 * CHANS bytes
+        const uint32_t delta = (uint32_t)((uintptr_t)ptr & 15u);
+        const uint4* a = reinterpret_cast<const uint4*>(ptr - delta);
+        uint32_t W[4 * kChunks + 1];
+#pragma unroll
+        for (int j = 0; j < kChunks; j++) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (16u * j < nbytes + delta) v = __ldg(a + j);
+            W[4 * j] = v.x; W[4 * j + 1] = v.y; W[4 * j + 2] = v.z; W[4 * j + 3] = v.w;
+        }
+        W[4 * kChunks] = 0u;
+        const uint32_t r = (delta & 3u) * 8u;
+        switch (delta >> 2) {                                 // warp-uniform
+        case 0:
+#pragma unroll
+            for (int i = 0; i < kWords; i++) out[i] = __funnelshift_r(W[i], W[i + 1], r);
+            break;
+        case 1:
+#pragma unroll
+            for (int i = 0; i < kWords; i++) out[i] = __funnelshift_r(W[i + 1], W[i + 2], r);
+            break;
+        case 2:
+#pragma unroll
+            for (int i = 0; i < kWords; i++) out[i] = __funnelshift_r(W[i + 2], W[i + 3], r);
+            break;
+        default:
+#pragma unroll
+            for (int i = 0; i < kWords; i++) out[i] = __funnelshift_r(W[i + 3], W[i + 4], r);
+            break;
+        }
+        if (nbytes < 16u * CHANS) {                           // the lane that holds the end of the scanline: zero the bytes beyond it
+#pragma unroll
+            for (int i = 0; i < kWords; i++) {
+                const uint32_t have = nbytes > 4u * i ? nbytes - 4u * i : 0u;
+                out[i] = have >= 4u ? out[i] : (have ? (out[i] & ((1u << (8u * have)) - 1u)) : 0u);
+            }
+        }
+    }
+
+    template <bool kAdler>
+    __device__ __forceinline__ void consume(bool have_prev, uint32_t, uint32_t step, uint32_t bpl, uint32_t lane, uint8_t*,
+                                            uint32_t (&dw)[kWords], uint32_t& sumA, unsigned long long& sumB) const
+    {
+        // cur / prev are passed through the object (the staging variants get them in prefetch)
+        const uint32_t lane_base = (step * (uint32_t)kStep16 + lane * (uint32_t)kPix16) * CHANS;
+        const uint32_t nbytes = lane_base < bpl ? min(16u * CHANS, bpl - lane_base) : 0u;
+        if (nbytes) {
+            load_lane(cur_ + lane_base, nbytes, dw);
+            if (have_prev) {
+                uint32_t pw[kWords];
+                load_lane(prev_ + lane_base, nbytes, pw);
+#pragma unroll
+                for (int i = 0; i < kWords; i++) dw[i] = vsub4(dw[i], pw[i]);
+                if (nbytes < 16u * CHANS) {                   // vsub4 of zero padding stays zero, nothing to fix
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kWords; i++) dw[i] = 0u;
+        }
+        if (kAdler) {
+#pragma unroll
+            for (int i = 0; i < CHANS; i++) {
+                uint32_t t1 = __dp4a(dw[4 * i], 0x01010101u, 0u), t2 = __dp4a(dw[4 * i], 0x03020100u, 0u);
+                t1 = __dp4a(dw[4 * i + 1], 0x01010101u, t1); t2 = __dp4a(dw[4 * i + 1], 0x07060504u, t2);
+                t1 = __dp4a(dw[4 * i + 2], 0x01010101u, t1); t2 = __dp4a(dw[4 * i + 2], 0x0B0A0908u, t2);
+                t1 = __dp4a(dw[4 * i + 3], 0x01010101u, t1); t2 = __dp4a(dw[4 * i + 3], 0x0F0E0D0Cu, t2);
+                sumA += t1;
+                sumB += (unsigned long long)(lane_base + 16u * i) * t1 + t2;
+            }
+        }
+    }
+    __device__ __forceinline__ static void pixels(const uint32_t (&dw)[kWords], uint32_t (&px)[16]) { Walk16Tma<CHANS>::pixels(dw, px); }
+    __device__ __forceinline__ void bind(const uint8_t* cur, const uint8_t* prev) { cur_ = cur; prev_ = prev; }
+    const uint8_t* cur_ = nullptr; const uint8_t* prev_ = nullptr;
 };
 
 // RGB: linear TMA tile (48-byte lane stride is bank-conflict free for 128-bit reads); RGBA: padded cp.async tile.

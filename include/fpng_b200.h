@@ -166,6 +166,17 @@ FPNGB_API int fpngb_create_dynamic_block_prefix(const uint64_t* counts288, uint3
                                                 uint32_t* codes288, uint8_t* sizes288);
 FPNGB_API int fpngb_set_static_table(uint32_t chans, const uint8_t* prefix, size_t nbytes, uint32_t bit_buf, uint32_t bit_buf_size);
 
+/* General-PNG fallback hook (the reference documents the pattern in src/fpng.h:79-91: "if FPNG_DECODE_NOT_FPNG is
+ * returned, fall back to a general purpose PNG decoder").  When a decoder is registered, the C++ wrappers
+ * fpng::fpng_decode_memory / fpng_decode_file (include/fpng.h) call it for files the fpng decoder rejects with
+ * FPNG_DECODE_NOT_FPNG and return its pixels with FPNG_DECODE_SUCCESS.  The callback returns 0 on success and hands over a
+ * malloc()ed buffer of w*h*desired_chans bytes (freed by the library); the C-ABI decode entry points are unaffected and keep
+ * returning FPNGB_DECODE_NOT_FPNG.  Pass NULL to unregister. */
+typedef int (*fpngb_fallback_decoder)(const void* file, uint32_t size, uint32_t desired_chans, void* user,
+                                      void** pixels, uint32_t* w, uint32_t* h, uint32_t* chans_in_file);
+FPNGB_API void fpngb_set_fallback_decoder(fpngb_fallback_decoder fn, void* user);
+FPNGB_API fpngb_fallback_decoder fpngb_get_fallback_decoder(void** user);
+
 /* Pinned host memory helpers for callers that want full PCIe bandwidth through the *_host entry points. */
 FPNGB_API void* fpngb_host_alloc(size_t bytes);
 FPNGB_API void fpngb_host_free(void* p);

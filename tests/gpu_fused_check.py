@@ -5,12 +5,18 @@ import numpy as np, torch
 import imagegen, fpng_b200
 from oracle.pyoracle import Oracle
 o = Oracle(); fpng_b200.fpng_init()
+from fpng_b200._lib import lib
+L = lib()
+mode = sys.argv[1] if len(sys.argv) > 1 else "inline"
+L.fpngb_debug_inline_crc(1 if mode == "inline" else 0)
+L.fpngb_debug_disable_fused(1 if mode == "old" else 0)
+print("mode", mode)
 bad = 0; n = 0
-shapes = [(16, 1), (16, 2), (32, 3), (512, 9), (528, 17), (1024, 5), (1040, 33), (1920, 8), (2048, 4), (4096, 3), (4080, 7), (3840, 5), (64, 300), (1536, 11)]
+shapes = [(16, 1), (16, 2), (32, 3), (512, 9), (528, 17), (1024, 5), (1040, 33), (1920, 8), (2048, 4), (4096, 3), (4080, 7), (3840, 5), (64, 300), (1536, 11),
+          (1, 1), (5, 3), (85, 2), (687, 41), (513, 6), (2049, 3), (4095, 2), (341, 25)]
 for kind in ('g1', 'g0', 'runs', 'g2', 'mut', 'zero'):
     for (w, h) in shapes:
         for c in (3, 4):
-            if (w * c) % 16: continue
             for flags in (0, 1):
                 imgs = np.stack([imagegen.make(kind, w, h, c, 3 + i) for i in range(3)])
                 out, sizes = fpng_b200.encode_batch_device(torch.from_numpy(imgs).cuda(), flags)

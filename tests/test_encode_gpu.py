@@ -246,3 +246,50 @@ def test_random_dimension_fuzz_like_reference_E(gpu, oracle):
                 assert ok and png == oracle.encode(img2, w, h, c, flags), (w, h, c, flags)
                 st, px, *_ = gpu.fpng_decode_memory(png, 7 - c)
                 assert st == 0
+
+
+@pytest.mark.parametrize("mode", ["fused+inline_crc", "fused", "two_kernel"])
+def test_encoder_generations_agree_with_oracle(gpu, oracle, mode):
+    """The single-pass encoder (encode_fused.cu: decoupled look-back, lane-local bit strings, in-kernel CRC partials), the same
+    with the file-reading CRC kernel, and the two-kernel scan + pack encoder must all write the reference's bytes."""
+    import torch
+    from fpng_b200._lib import lib
+    L = lib()
+    L.fpngb_debug_inline_crc(1 if mode == "fused+inline_crc" else 0)
+    L.fpngb_debug_disable_fused(1 if mode == "two_kernel" else 0)
+    try:
+        # aligned and unaligned scanlines (the single-pass kernel has a staged-tile and a direct-load variant), partial units,
+        # widths beyond its reach (> 4096: two-kernel encoder), one-pixel and one-row images
+        shapes = [(16, 1), (16, 2), (16, 40), (32, 3), (512, 9), (528, 17), (1024, 5), (1040, 33), (1920, 8), (2048, 4), (4096, 3), (4080, 7),
+                  (3840, 5), (64, 300), (1536, 11), (4112, 3), (1, 1), (1, 9), (2, 2), (5, 3), (85, 2), (86, 2), (687, 41), (513, 6), (1023, 4),
+                  (2049, 3), (4095, 2), (4097, 2), (341, 25)]
+        for kind in ("g1", "g0", "runs", "g2", "mut", "zero"):
+            for (w, h) in shapes:
+                for c in (3, 4):
+                    for flags in (0, 1):
+                        imgs = np.stack([imagegen.make(kind, w, h, c, 3 + i) for i in range(3)])
+                        out, sizes = gpu.encode_batch_device(torch.from_numpy(imgs).cuda(), flags)
+                        torch.cuda.synchronize()
+                        sz = sizes.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+                        oh = out.cpu().numpy()
+                        for i in range(3):
+                            assert oh[i, : sz[i]].tobytes() == oracle.encode(imgs[i], w, h, c, flags), (mode, kind, w, h, c, flags, i)
+    finally:
+        L.fpngb_debug_inline_crc(1)
+        L.fpngb_debug_disable_fused(0)
+
+
+def test_single_pass_encoder_many_groups(gpu, ref):
+    """Long look-back chains: tall images (thousands of row groups per image) and a batch mixing compressible images with
+    ones that fall back to stored blocks after the single-pass kernel already wrote into their buffers."""
+    import torch
+    for (w, h, c) in ((512, 6000, 3), (1024, 3000, 4), (4096, 700, 4)):
+        kinds = ["g1", "g2", "g0", "runs", "g2", "mut"]
+        imgs = np.stack([imagegen.make(k, w, h, c, i) for i, k in enumerate(kinds)])
+        for flags in (0, 1):
+            out, sizes = gpu.encode_batch_device(torch.from_numpy(imgs).cuda(), flags)
+            torch.cuda.synchronize()
+            sz = sizes.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            oh = out.cpu().numpy()
+            for i in range(len(kinds)):
+                assert oh[i, : sz[i]].tobytes() == ref.encode(imgs[i], w, h, c, flags), (w, h, c, flags, kinds[i])
