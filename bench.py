@@ -285,6 +285,8 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     fpng_b200.fpng_init(local)
     L = lib()
+    # multi-rank runs: keep this rank's host threads and pinned staging on the GPU's own NUMA node (e2e legs are PCIe-bound)
+    numa_node = L.fpngb_bind_host_thread_to_device_numa() if world > 1 else -1
     L.fpngb_profile_enable.argtypes = [C.c_int]
     L.fpngb_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int]
 
@@ -429,10 +431,20 @@ def run_ours(args, wl):
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         dms = float(td.item()) / dsteps
         dec_bytes = out_bytes + n * w * h * c
+        # per-kernel device times of one more decode call (CUDA events between the launches)
+        L.fpngb_decode_profile_enable.argtypes = [C.c_int]
+        L.fpngb_decode_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int]
+        L.fpngb_decode_profile_enable(1)
+        dstep()
+        torch.cuda.synchronize(dev)
+        dprof = (C.c_float * 6)()
+        have_dprof = L.fpngb_decode_profile_read(dprof, 6)
+        L.fpngb_decode_profile_enable(0)
         line["decode"] = {"value": world * n * w * h / MP / (dms / 1e3), "unit": "MP/s", "ms_per_step": dms, "steps": dsteps,
                           "pixels_match_input": dec_ok, "algorithmic_gbs": dec_bytes / 1e9 / (dms / 1e3),
                           "frac_of_peak": dec_bytes / 1e9 / (dms / 1e3) / peak,
-                          "input": dec_input}
+                          "input": dec_input,
+                          "kernels_ms": dict(zip(["prepare", "scan", "link", "write", "stored", "unfilter"], [float(v) for v in dprof])) if have_dprof else None}
         # end to end through the C ABI with host buffers: files (pinned) -> H2D -> kernels -> D2H pixels (pinned)
         hfiles = torch.zeros((n, fstride), dtype=torch.uint8).pin_memory()
         hfiles.copy_(files_dev.cpu())
@@ -558,6 +570,8 @@ def run_ours(args, wl):
     line["e2e"] = {"value": world * n_e2e * w * h * e2e_steps / MP / dt, "unit": "MP/s", "h2d_bytes_per_step": n_e2e * w * h * c,
                    "d2h_bytes_per_step": int(hsizes.astype(np.int64).sum()) + 4 * n_e2e, "images_per_step": n_e2e, "steps": e2e_steps,
                    "api": "fpngb_encode_batch_host (C ABI, pinned host buffers, blocking)", "timer": "host wall clock around the blocking calls",
+                   "numa_node_bound": numa_node,
+                   "per_rank_gbs": {"h2d": n_e2e * w * h * c * e2e_steps / 1e9 / dt, "d2h": int(hsizes.astype(np.int64).sum()) * e2e_steps / 1e9 / dt},
                    "matches_device_path": bool(e2e_ok)}
 
     if rank == 0 and world == 1 and not args.no_cpu:

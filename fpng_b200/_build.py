@@ -13,8 +13,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3", "-shared",
 ]
-# comm.cu talks to NCCL (system libnccl.so.2 2.27.3; inside a torch process the already loaded, ABI-compatible bundled one is used)
-LINK_FLAGS = ["-lnccl"]
+# comm.cu binds NCCL at run time (dlopen: the process's own copy if it has one, else the system libnccl.so.2); nothing is linked
+LINK_FLAGS = ["-ldl"]
 
 
 def sources() -> list[str]:

@@ -16,11 +16,52 @@
 #include "../../include/fpng_b200.h"
 #include "runtime.h"
 #include <nccl.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
 #include <vector>
 
 namespace fpngb {
+
+// NCCL is bound at run time, on the first fpngb_comm_* call: a process that already holds an NCCL (a PyTorch process: its
+// bundled libnccl.so.2) keeps using that one, others load the system library.  Linking libnccl directly would make THIS
+// library pull the system NCCL into the process at load time and break a later `import torch` whose libtorch needs newer
+// symbols from its own copy (same soname).
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*CommCount)(const ncclComm_t, int*);
+    ncclResult_t (*CommUserRank)(const ncclComm_t, int*);
+    ncclResult_t (*CommCuDevice)(const ncclComm_t, int*);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    bool ok = false;
+};
+static NcclApi g_nccl;
+
+static bool nccl_bind()
+{
+    if (g_nccl.ok) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);               // the copy the process already uses, if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    bool all = true;
+#define FPNGB_NCCL_SYM(field, name) do { *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) all = false; } while (0)
+    FPNGB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); FPNGB_NCCL_SYM(CommInitRank, "ncclCommInitRank"); FPNGB_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    FPNGB_NCCL_SYM(CommCount, "ncclCommCount"); FPNGB_NCCL_SYM(CommUserRank, "ncclCommUserRank"); FPNGB_NCCL_SYM(CommCuDevice, "ncclCommCuDevice");
+    FPNGB_NCCL_SYM(AllGather, "ncclAllGather"); FPNGB_NCCL_SYM(AllReduce, "ncclAllReduce"); FPNGB_NCCL_SYM(Send, "ncclSend"); FPNGB_NCCL_SYM(Recv, "ncclRecv");
+    FPNGB_NCCL_SYM(GroupStart, "ncclGroupStart"); FPNGB_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+#undef FPNGB_NCCL_SYM
+    g_nccl.ok = all;
+    return all;
+}
+#define FPNGB_NEED_NCCL() do { if (!nccl_bind()) return FPNGB_ERR_INTERNAL; } while (0)
 
 struct Comm {
     ncclComm_t nccl = nullptr;
@@ -119,9 +160,10 @@ extern "C" {
 int fpngb_comm_unique_id(void* id128)
 {
     if (!id128) return FPNGB_ERR_INVALID_ARG;
+    FPNGB_NEED_NCCL();
     static_assert(sizeof(ncclUniqueId) == FPNGB_UNIQUE_ID_BYTES, "ncclUniqueId size");
     ncclUniqueId id;
-    FPNGB_NCCL_OK(ncclGetUniqueId(&id));
+    FPNGB_NCCL_OK(g_nccl.GetUniqueId(&id));
     memcpy(id128, &id, sizeof id);
     return FPNGB_OK;
 }
@@ -131,12 +173,13 @@ int fpngb_comm_init(const void* id128, int nranks, int rank)
     Context& c = context();
     if (!c.ready) return FPNGB_ERR_NOT_INITIALIZED;
     if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return FPNGB_ERR_INVALID_ARG;
+    FPNGB_NEED_NCCL();
     std::lock_guard<std::mutex> lk(c.mu);
     if (g_comm.nccl) return FPNGB_ERR_INVALID_ARG;            // one communicator per process; destroy it first
     FPNGB_CUDA_OK(cudaSetDevice(c.device));
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
-    FPNGB_NCCL_OK(ncclCommInitRank(&g_comm.nccl, nranks, id, rank));
+    FPNGB_NCCL_OK(g_nccl.CommInitRank(&g_comm.nccl, nranks, id, rank));
     g_comm.owned = true; g_comm.nranks = nranks; g_comm.rank = rank;
     return FPNGB_OK;
 }
@@ -146,13 +189,14 @@ int fpngb_comm_adopt(void* nccl_comm)
     Context& c = context();
     if (!c.ready) return FPNGB_ERR_NOT_INITIALIZED;
     if (!nccl_comm) return FPNGB_ERR_INVALID_ARG;
+    FPNGB_NEED_NCCL();
     std::lock_guard<std::mutex> lk(c.mu);
     if (g_comm.nccl) return FPNGB_ERR_INVALID_ARG;
     ncclComm_t comm = (ncclComm_t)nccl_comm;
     int n = 0, r = 0, dev = -1;
-    FPNGB_NCCL_OK(ncclCommCount(comm, &n));
-    FPNGB_NCCL_OK(ncclCommUserRank(comm, &r));
-    FPNGB_NCCL_OK(ncclCommCuDevice(comm, &dev));
+    FPNGB_NCCL_OK(g_nccl.CommCount(comm, &n));
+    FPNGB_NCCL_OK(g_nccl.CommUserRank(comm, &r));
+    FPNGB_NCCL_OK(g_nccl.CommCuDevice(comm, &dev));
     if (dev != c.device) return FPNGB_ERR_INVALID_ARG;
     g_comm.nccl = comm; g_comm.owned = false; g_comm.nranks = n; g_comm.rank = r;
     return FPNGB_OK;
@@ -167,7 +211,7 @@ int fpngb_comm_destroy(void)
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
     comm_release_windows(g_comm);
-    if (g_comm.owned) ncclCommDestroy(g_comm.nccl);
+    if (g_comm.owned) g_nccl.CommDestroy(g_comm.nccl);
     g_comm.nccl = nullptr; g_comm.nranks = 0; g_comm.rank = -1; g_comm.owned = false;
     return FPNGB_OK;
 }
@@ -212,7 +256,7 @@ int fpngb_gather_setup(size_t window_bytes, uint32_t max_files_per_rank)
     FPNGB_CUDA_OK(cudaMalloc(&d_slots, sizeof(Slot) * m.nranks));
     FPNGB_CUDA_OK(cudaMemcpy(d_slots + m.rank, &my_slot, sizeof my_slot, cudaMemcpyHostToDevice));
     cudaStream_t s = c.stream;
-    ncclResult_t nr = ncclAllGather(d_slots + m.rank, d_slots, sizeof(Slot), ncclChar, m.nccl, s);
+    ncclResult_t nr = g_nccl.AllGather(d_slots + m.rank, d_slots, sizeof(Slot), ncclChar, m.nccl, s);
     if (nr != ncclSuccess) { cudaFree(d_slots); return 2000 + (int)nr; }
     FPNGB_CUDA_OK(cudaStreamSynchronize(s));
     std::vector<Slot> all(m.nranks);
@@ -229,7 +273,7 @@ int fpngb_gather_setup(size_t window_bytes, uint32_t max_files_per_rank)
     // every rank must take the same path: agree on min(ok)
     int h_ok = ok ? 1 : 0;
     FPNGB_CUDA_OK(cudaMemcpy(m.d_flag, &h_ok, sizeof(int), cudaMemcpyHostToDevice));
-    FPNGB_NCCL_OK(ncclAllReduce(m.d_flag, m.d_flag + 1, 1, ncclInt, ncclMin, m.nccl, s));
+    FPNGB_NCCL_OK(g_nccl.AllReduce(m.d_flag, m.d_flag + 1, 1, ncclInt, ncclMin, m.nccl, s));
     FPNGB_CUDA_OK(cudaStreamSynchronize(s));
     FPNGB_CUDA_OK(cudaMemcpy(&h_ok, m.d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost));
     m.p2p = h_ok == 1;
@@ -256,7 +300,7 @@ int fpngb_gather_encoded_device(const void* d_files, size_t stride, const uint32
     const uint32_t slots = (uint32_t)m.nranks * m.nmax;
 
     pad_sizes_kernel<<<(m.nmax + 255) / 256, 256, 0, s>>>(d_sizes, n_local, m.nmax, m.d_my_sizes);
-    FPNGB_NCCL_OK(ncclAllGather(m.d_my_sizes, m.d_all_sizes, m.nmax, ncclUint32, m.nccl, s));
+    FPNGB_NCCL_OK(g_nccl.AllGather(m.d_my_sizes, m.d_all_sizes, m.nmax, ncclUint32, m.nccl, s));
     gather_offsets_kernel<<<1, 1024, 0, s>>>(m.d_all_sizes, slots, m.d_offsets);
     count_launch(2);
     if (m.p2p) {
@@ -269,7 +313,7 @@ int fpngb_gather_encoded_device(const void* d_files, size_t stride, const uint32
         }
         FPNGB_CUDA_OK(cudaGetLastError());
         // completion barrier: returns on a receiver only after every sender's push kernel has completed
-        FPNGB_NCCL_OK(ncclAllReduce(m.d_flag, m.d_flag + 1, 1, ncclInt, ncclSum, m.nccl, s));
+        FPNGB_NCCL_OK(g_nccl.AllReduce(m.d_flag, m.d_flag + 1, 1, ncclInt, ncclSum, m.nccl, s));
     } else {
         // fallback without peer windows: compact locally, then grouped send/recv with host-side byte counts (one synchronisation)
         std::vector<unsigned long long> h_off(slots + 1);
@@ -297,14 +341,14 @@ int fpngb_gather_encoded_device(const void* d_files, size_t stride, const uint32
                                                         m.d_peer, m.rank, (size_t)-1);
                 count_launch(1);
             }
-            FPNGB_NCCL_OK(ncclGroupStart());
+            FPNGB_NCCL_OK(g_nccl.GroupStart());
             for (int r = 0; r < m.nranks; r++) {
                 if (r == m.rank) continue;
                 const size_t rb = (size_t)(rank_end(r) - rank_begin(r));
-                if (i_receive && rb) FPNGB_NCCL_OK(ncclRecv(m.window + rank_begin(r), rb, ncclChar, r, m.nccl, s));
-                if ((dst_rank < 0 || dst_rank == r) && my_bytes) FPNGB_NCCL_OK(ncclSend(my_dst, my_bytes, ncclChar, r, m.nccl, s));
+                if (i_receive && rb) FPNGB_NCCL_OK(g_nccl.Recv(m.window + rank_begin(r), rb, ncclChar, r, m.nccl, s));
+                if ((dst_rank < 0 || dst_rank == r) && my_bytes) FPNGB_NCCL_OK(g_nccl.Send(my_dst, my_bytes, ncclChar, r, m.nccl, s));
             }
-            FPNGB_NCCL_OK(ncclGroupEnd());
+            FPNGB_NCCL_OK(g_nccl.GroupEnd());
         }
     }
     FPNGB_CUDA_OK(cudaGetLastError());

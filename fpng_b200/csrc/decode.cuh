@@ -42,5 +42,7 @@ struct DecodeParams {
 };
 
 void launch_decode(const DecodeParams& p, uint32_t n, uint32_t desired, cudaStream_t s);
+void decode_profile_enable(bool on);
+int decode_profile_read(float* ms, int n);
 
 }  // namespace fpngb

@@ -228,6 +228,7 @@ __device__ __forceinline__ Stream open_stream(const uint8_t* file, const FileDes
 
 struct Cursor {
     unsigned long long buf; uint32_t cnt, widx;
+    uint32_t ahead;            // the next stream word, loaded one refill early so that its latency overlaps the decoding of ~32 bits
     __device__ __forceinline__ void seek(const Stream& st, unsigned long long abs_bit)
     {
         widx = (uint32_t)(abs_bit >> 5);
@@ -235,10 +236,14 @@ struct Cursor {
         const uint32_t lo = __ldg(st.words + min(widx, st.max_widx)), hi = __ldg(st.words + min(widx + 1u, st.max_widx));
         buf = (((unsigned long long)hi << 32) | lo) >> sh;
         cnt = 64u - sh; widx += 2u;
+        ahead = __ldg(st.words + min(widx, st.max_widx));
     }
     __device__ __forceinline__ void refill(const Stream& st)
     {
-        if (cnt <= 32u) { buf |= (unsigned long long)__ldg(st.words + min(widx, st.max_widx)) << cnt; cnt += 32u; widx++; }
+        if (cnt <= 32u) {
+            buf |= (unsigned long long)ahead << cnt; cnt += 32u; widx++;
+            ahead = __ldg(st.words + min(widx, st.max_widx));
+        }
     }
     __device__ __forceinline__ void skip(uint32_t n) { buf >>= n; cnt -= n; }
 };
@@ -654,7 +659,7 @@ __global__ void __launch_bounds__(128) unfilter_kernel(DecodeParams p)
 #pragma unroll
     for (int i = 0; i < SRC; i++) acc[i] = 0;
     const bool summing = !st.stored;
-    constexpr int kRowsAhead = 4;                  // independent loads in flight per thread
+    constexpr int kRowsAhead = 8;                  // independent loads in flight per thread (8 rows x 12-16 bytes: enough bytes in flight at 256 files)
     for (uint32_t y0 = 0; y0 < h; y0 += kRowsAhead) {
         uint32_t dd[kRowsAhead][SRC];
 #pragma unroll
@@ -708,16 +713,42 @@ __global__ void decode_status_kernel(DecodeParams p, uint32_t n)
     if (f < n) p.d_status[f] = p.state[f].status ? 1u /*FPNG_DECODE_NOT_FPNG*/ : 0u;
 }
 
+// Optional per-kernel timing of the decode pipeline (bench.py): events recorded between the launches of the most recent
+// call while profiling is on; fpngb_decode_profile_read() returns the device times of prepare, scan, link, write, stored,
+// unfilter (ms).
+static bool g_dec_profile = false;
+static cudaEvent_t g_dec_ev[8];
+static bool g_dec_ev_ready = false, g_dec_ev_valid = false;
+void decode_profile_enable(bool on)
+{
+    g_dec_profile = on;
+    if (on && !g_dec_ev_ready) { for (int i = 0; i < 8; i++) cudaEventCreate(&g_dec_ev[i]); g_dec_ev_ready = true; }
+}
+int decode_profile_read(float* ms, int n)
+{
+    if (!g_dec_ev_valid) return 0;
+    cudaEventSynchronize(g_dec_ev[6]);
+    for (int i = 0; i < n && i < 6; i++) { ms[i] = 0.f; cudaEventElapsedTime(&ms[i], g_dec_ev[i], g_dec_ev[i + 1]); }
+    return 1;
+}
+#define DEC_MARK(i) do { if (g_dec_profile && g_dec_ev_ready) cudaEventRecord(g_dec_ev[i], s); } while (0)
+
 void launch_decode(const DecodeParams& p, uint32_t n, uint32_t desired, cudaStream_t s)
 {
+    DEC_MARK(0);
     decode_prepare_kernel<<<n, 32, 0, s>>>(p);
+    DEC_MARK(1);
     const uint32_t sub_blocks = (p.subs_per_file + kDecThreads - 1) / kDecThreads;
     dim3 gsub(sub_blocks, n);
     decode_scan_kernel<<<gsub, kDecThreads, 0, s>>>(p);
+    DEC_MARK(2);
     decode_link_kernel<<<n, kLinkThreads, 0, s>>>(p);
+    DEC_MARK(3);
     decode_write_kernel<<<gsub, kDecThreads, 0, s>>>(p);
+    DEC_MARK(4);
     dim3 gs((p.h + 7) / 8, n);
     decode_stored_kernel<<<gs, 256, 0, s>>>(p);
+    DEC_MARK(5);
     const uint32_t groups = (p.w + 3) / 4;
     dim3 gu((groups + 127) / 128, n);
     if (p.chans == 3 && desired == 3) unfilter_kernel<3, 3><<<gu, 128, 0, s>>>(p);
@@ -725,6 +756,8 @@ void launch_decode(const DecodeParams& p, uint32_t n, uint32_t desired, cudaStre
     else if (desired == 3) unfilter_kernel<4, 3><<<gu, 128, 0, s>>>(p);
     else unfilter_kernel<4, 4><<<gu, 128, 0, s>>>(p);
     decode_status_kernel<<<(n + 127) / 128, 128, 0, s>>>(p, n);
+    DEC_MARK(6);
+    if (g_dec_profile && g_dec_ev_ready) g_dec_ev_valid = true;
 }
 
 }  // namespace fpngb

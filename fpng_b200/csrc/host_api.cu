@@ -14,6 +14,7 @@
 #include <atomic>
 #include <mutex>
 #include <new>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -748,6 +749,46 @@ int fpngb_set_static_table(uint32_t chans, const uint8_t* prefix, size_t nbytes,
     c.h_static_books[chans == 4 ? 1 : 0] = cb;
     FPNGB_CUDA_OK(cudaMemcpy(c.d_static_books + (chans == 4 ? 1 : 0), &cb, sizeof cb, cudaMemcpyHostToDevice));
     return FPNGB_OK;
+}
+
+// Binds the calling thread (and the threads it creates later) to the CPUs of the NUMA node the library's GPU hangs off, so that
+// pinned staging buffers allocated afterwards (first touch) and the copy-issuing thread sit next to the GPU's PCIe root port.
+// With 8 ranks on a two-socket host this is what keeps H2D/D2H of the *_host entry points from crossing the socket
+// interconnect.  Returns the NUMA node (>= 0), or -1 when the topology is not exposed (single node, container without
+// sysfs): then nothing is changed.
+int fpngb_bind_host_thread_to_device_numa(void)
+{
+    if (!g_ctx.ready) return -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, g_ctx.device) != cudaSuccess) return -1;
+    for (char* q = bus; *q; q++) if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    char list[4096] = {0};
+    const size_t got = fread(list, 1, sizeof list - 1, f);
+    fclose(f);
+    if (!got) return -1;
+    cpu_set_t set; CPU_ZERO(&set);
+    cpu_set_t allowed; CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return -1;
+    int count = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        if (sscanf(tok, "%d-%d", &a, &b) == 2) { } else if (sscanf(tok, "%d", &a) == 1) b = a; else continue;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &set); count++; }
+    }
+    if (!count) return -1;                                             // the node's CPUs are outside this process's cpuset: leave it alone
+    if (sched_setaffinity(0, sizeof set, &set) != 0) return -1;
+    return node;
 }
 
 void* fpngb_host_alloc(size_t bytes)

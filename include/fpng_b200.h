@@ -177,6 +177,12 @@ typedef int (*fpngb_fallback_decoder)(const void* file, uint32_t size, uint32_t 
 FPNGB_API void fpngb_set_fallback_decoder(fpngb_fallback_decoder fn, void* user);
 FPNGB_API fpngb_fallback_decoder fpngb_get_fallback_decoder(void** user);
 
+/* Pins the calling thread to the CPUs of the NUMA node of the library's GPU (sysfs: the GPU's PCI device -> numa_node ->
+ * cpulist), so that pinned buffers allocated afterwards and the thread that issues the H2D/D2H copies are local to the GPU's
+ * PCIe root port.  Call once per rank after fpngb_init(), before allocating staging memory.  Returns the node, or -1 if the
+ * topology is not visible (nothing changed). */
+FPNGB_API int fpngb_bind_host_thread_to_device_numa(void);
+
 /* Pinned host memory helpers for callers that want full PCIe bandwidth through the *_host entry points. */
 FPNGB_API void* fpngb_host_alloc(size_t bytes);
 FPNGB_API void fpngb_host_free(void* p);
