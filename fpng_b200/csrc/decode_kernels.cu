@@ -214,7 +214,29 @@ struct Stream {
     const uint32_t* words;     // aligned base
     uint32_t max_widx;         // last readable word index (reads beyond are clamped: garbage but in bounds)
     uint32_t bit0;             // aligned-stream bit position of zlib bit 0 (0, 8, 16 or 24)
+    // optional shared-memory window over words [sw_base, sw_base + sw_count): the scan and write kernels stage the 32 KiB of
+    // stream their 256 subsequences walk (coalesced loads, one pad word per 32 so that threads 32 words apart hit different
+    // banks); a refill is then a ~30-cycle shared load instead of an L1/L2 round trip in the middle of a dependent chain
+    const uint32_t* swin; uint32_t sw_base, sw_count;
+    __device__ __forceinline__ uint32_t word(uint32_t widx) const
+    {
+        const uint32_t si = widx - sw_base;
+        if (si < sw_count) return swin[si + (si >> 5)];
+        return __ldg(words + min(widx, max_widx));
+    }
 };
+constexpr uint32_t kWinLead = 8, kWinTail = 8;                                   // words before / after the CTA's 256 subsequences
+constexpr uint32_t kWinWords = kWinLead + kDecThreads * (kSubBits / 32) + kWinTail;
+constexpr uint32_t kWinSmemWords = kWinWords + kWinWords / 32 + 1;
+
+// cooperative load of the CTA's stream window; `first_sub` = index of the CTA's first subsequence
+__device__ __forceinline__ void stage_window(Stream& st, uint32_t* s_win, unsigned long long first_sub)
+{
+    const unsigned long long w0 = first_sub * (kSubBits / 32);
+    const uint32_t base = (uint32_t)(w0 >= kWinLead ? w0 - kWinLead : 0ull);
+    for (uint32_t i = threadIdx.x; i < kWinWords; i += blockDim.x) s_win[i + (i >> 5)] = __ldg(st.words + min(base + i, st.max_widx));
+    st.swin = s_win; st.sw_base = base; st.sw_count = kWinWords;
+}
 
 __device__ __forceinline__ Stream open_stream(const uint8_t* file, const FileDesc& fd)
 {
@@ -223,6 +245,7 @@ __device__ __forceinline__ Stream open_stream(const uint8_t* file, const FileDes
     st.words = reinterpret_cast<const uint32_t*>(file + (zofs & ~3u));
     st.bit0 = (zofs & 3u) * 8u;
     st.max_widx = ((fd.file_size + 3u) >> 2) - 1u - (zofs >> 2);     // file buffers are padded to a multiple of 4
+    st.swin = nullptr; st.sw_base = 0; st.sw_count = 0;
     return st;
 }
 
@@ -233,16 +256,16 @@ struct Cursor {
     {
         widx = (uint32_t)(abs_bit >> 5);
         const uint32_t sh = (uint32_t)abs_bit & 31u;
-        const uint32_t lo = __ldg(st.words + min(widx, st.max_widx)), hi = __ldg(st.words + min(widx + 1u, st.max_widx));
+        const uint32_t lo = st.word(widx), hi = st.word(widx + 1u);
         buf = (((unsigned long long)hi << 32) | lo) >> sh;
         cnt = 64u - sh; widx += 2u;
-        ahead = __ldg(st.words + min(widx, st.max_widx));
+        ahead = st.word(widx);
     }
     __device__ __forceinline__ void refill(const Stream& st)
     {
         if (cnt <= 32u) {
             buf |= (unsigned long long)ahead << cnt; cnt += 32u; widx++;
-            ahead = __ldg(st.words + min(widx, st.max_widx));
+            ahead = st.word(widx);
         }
     }
     __device__ __forceinline__ void skip(uint32_t n) { buf >>= n; cnt -= n; }
@@ -417,16 +440,19 @@ __device__ __forceinline__ FileSpan file_span(const DecodeState& st, const Strea
 
 __global__ void __launch_bounds__(kDecThreads) decode_scan_kernel(DecodeParams p)
 {
-    __shared__ uint32_t s_lut[4096];
+    extern __shared__ __align__(16) uint32_t dec_smem[];
+    uint32_t* s_lut = dec_smem;                       // [4096]
+    uint32_t* s_win = dec_smem + 4096;                // [kWinSmemWords]
     const uint32_t f = blockIdx.y, tid = threadIdx.x;
     const DecodeState st = p.state[f];
     if (st.status || st.stored) return;
     const FileDesc fd = p.files[f];
-    const Stream sm = open_stream(p.d_files + (size_t)f * p.file_stride, fd);
+    Stream sm = open_stream(p.d_files + (size_t)f * p.file_stride, fd);
     const FileSpan sp = file_span(st, sm, fd);
     const unsigned long long g = sp.g0 + (unsigned long long)blockIdx.x * kDecThreads + tid;
     if (sp.g0 + (unsigned long long)blockIdx.x * kDecThreads > sp.g1) return;
     for (uint32_t i = tid; i < 4096; i += blockDim.x) s_lut[i] = p.luts[(size_t)f * 4096 + i];
+    stage_window(sm, s_win, sp.g0 + (unsigned long long)blockIdx.x * kDecThreads);
     __syncthreads();
     if (g > sp.g1) return;
     SubInfo* info = p.subs + (size_t)f * p.subs_per_file + (g - sp.g0);
@@ -566,15 +592,18 @@ __global__ void __launch_bounds__(kLinkThreads) decode_link_kernel(DecodeParams 
 
 __global__ void __launch_bounds__(kDecThreads) decode_write_kernel(DecodeParams p)
 {
-    __shared__ uint32_t s_lut[4096];
+    extern __shared__ __align__(16) uint32_t dec_smem[];
+    uint32_t* s_lut = dec_smem;                       // [4096]
+    uint32_t* s_win = dec_smem + 4096;                // [kWinSmemWords]
     const uint32_t f = blockIdx.y, tid = threadIdx.x;
     DecodeState* stp = p.state + f;
     if (stp->status || stp->stored) return;
     const FileDesc fd = p.files[f];
-    const Stream sm = open_stream(p.d_files + (size_t)f * p.file_stride, fd);
+    Stream sm = open_stream(p.d_files + (size_t)f * p.file_stride, fd);
     const FileSpan sp = file_span(*stp, sm, fd);
     if (sp.g0 + (unsigned long long)blockIdx.x * kDecThreads > sp.g1) return;
     for (uint32_t i = tid; i < 4096; i += blockDim.x) s_lut[i] = p.luts[(size_t)f * 4096 + i];
+    stage_window(sm, s_win, sp.g0 + (unsigned long long)blockIdx.x * kDecThreads);
     __syncthreads();
     const unsigned long long g = sp.g0 + (unsigned long long)blockIdx.x * kDecThreads + tid;
     if (g > sp.g1) return;
@@ -740,11 +769,14 @@ void launch_decode(const DecodeParams& p, uint32_t n, uint32_t desired, cudaStre
     DEC_MARK(1);
     const uint32_t sub_blocks = (p.subs_per_file + kDecThreads - 1) / kDecThreads;
     dim3 gsub(sub_blocks, n);
-    decode_scan_kernel<<<gsub, kDecThreads, 0, s>>>(p);
+    constexpr size_t kDecSmem = (4096 + kWinSmemWords) * 4;
+    FPNGB_SET_SMEM(decode_scan_kernel, kDecSmem);
+    FPNGB_SET_SMEM(decode_write_kernel, kDecSmem);
+    decode_scan_kernel<<<gsub, kDecThreads, kDecSmem, s>>>(p);
     DEC_MARK(2);
     decode_link_kernel<<<n, kLinkThreads, 0, s>>>(p);
     DEC_MARK(3);
-    decode_write_kernel<<<gsub, kDecThreads, 0, s>>>(p);
+    decode_write_kernel<<<gsub, kDecThreads, kDecSmem, s>>>(p);
     DEC_MARK(4);
     dim3 gs((p.h + 7) / 8, n);
     decode_stored_kernel<<<gs, 256, 0, s>>>(p);
