@@ -416,6 +416,81 @@ __device__ __forceinline__ SubScan decode_range(const Stream& st, const uint32_t
     return r;
 }
 
+// Write pass, lean form: decodes the tokens of one subsequence from its verified start and stores the delta bytes.
+// Output state is three 32-bit values (row, data column, pending-byte accumulator) and a row pointer; bytes are gathered into
+// aligned 32-bit stores (a thread's unaligned head bytes and a row's tail bytes go out singly, so neighbouring threads
+// never touch the same word).  Same acceptance rules as decode_range<true> (fpng.cpp:2264, 2302-2315, 2642, 2681-2691, 2727).
+template <int CHANS>
+__device__ __forceinline__ void decode_write_range(const Stream& st, const uint32_t* __restrict__ s_lut, unsigned long long abs_origin, uint32_t hi,
+                                                   uint8_t* __restrict__ delta, uint32_t pitch, uint32_t bpl, uint32_t h,
+                                                   unsigned long long out_pos, uint32_t tail, uint32_t* err)
+{
+    Cursor c; c.seek(st, abs_origin);
+    uint32_t rel = 0, lits = tail;
+    uint32_t row = (uint32_t)(out_pos / (bpl + 1ull));
+    const uint32_t col0 = (uint32_t)(out_pos % (bpl + 1ull));
+    bool need_filter = col0 == 0u;                     // the next byte of the filtered stream is the row's filter byte
+    uint32_t dcol = col0 ? col0 - 1u : 0u;             // data bytes of the current row already produced
+    uint8_t* rowp = delta + (size_t)row * pitch;
+    uint32_t acc = 0, nacc = 0;                        // pending bytes: data columns [dcol - nacc, dcol), first one 4-byte aligned
+
+#define FPNGB_EMIT(v) do { \
+        const uint32_t v__ = (v); \
+        if (nacc == 0u && (dcol & 3u)) rowp[dcol] = (uint8_t)v__;                                   /* unaligned head of this thread's range */ \
+        else { acc |= v__ << (8u * nacc); if (++nacc == 4u) { *reinterpret_cast<uint32_t*>(rowp + dcol - 3u) = acc; acc = 0u; nacc = 0u; } } \
+        if (++dcol == bpl) {                                                                          /* scanline complete */ \
+            for (uint32_t i__ = 0; i__ < nacc; i__++) rowp[dcol - nacc + i__] = (uint8_t)(acc >> (8u * i__)); \
+            acc = 0u; nacc = 0u; row++; rowp += pitch; dcol = 0u; need_filter = true; \
+        } \
+    } while (0)
+#define FPNGB_LITERAL(v) do { \
+        const uint32_t s__ = (v); \
+        lits = (lits >> 8) | (s__ << 24); \
+        if (need_filter) { if (row >= h || s__ != (row ? 2u : 0u)) { *err = 1; return; } need_filter = false; } \
+        else { if (row >= h) { *err = 1; return; } FPNGB_EMIT(s__); } \
+    } while (0)
+
+    while (rel < hi) {
+        c.refill(st);
+        const uint32_t e = s_lut[(uint32_t)c.buf & 4095u];
+        const uint32_t l0 = lut_len0(e), s = lut_sym0(e);
+        if (!l0) return;                                                   // invalid code: the link pass already flagged it
+        if (s < 256u) {
+            const uint32_t l1 = lut_len1(e);
+            const bool two = l1 && (rel + l0 < hi);
+            const uint32_t l = two ? l0 + l1 : l0;
+            c.skip(l); rel += l;
+            FPNGB_LITERAL(s);
+            if (two) FPNGB_LITERAL(lut_sym1(e));
+        } else if (s == 256u) {
+            break;
+        } else {
+            if (s > 285u) return;
+            c.skip(l0);
+            const uint32_t xb = c_len_xbits[s - 257u];
+            const uint32_t run = c_len_base[s - 257u] + ((uint32_t)c.buf & ((1u << xb) - 1u));
+            c.skip(xb + 1u);
+            rel += l0 + xb + 1u;
+            const bool bad = row >= h || need_filter || dcol < (uint32_t)CHANS || (dcol % CHANS) != 0u || (run % CHANS) != 0u || dcol + run > bpl;
+            if (bad) { *err = 1; return; }
+            const uint32_t px = CHANS == 4 ? lits : (lits >> 8);          // last CHANS literals, oldest in the low byte
+            if (CHANS == 4) {
+                // dcol % 4 == 0: nothing is pending, pixels are word aligned
+                uint32_t* d = reinterpret_cast<uint32_t*>(rowp + dcol);
+                const uint32_t npx = run >> 2;
+                for (uint32_t i = 0; i < npx; i++) d[i] = px;
+                dcol += run;
+                if (dcol == bpl) { row++; rowp += pitch; dcol = 0u; need_filter = true; }
+            } else {
+                for (uint32_t i = 0; i < run; i += 3) { FPNGB_EMIT(px & 0xFFu); FPNGB_EMIT((px >> 8) & 0xFFu); FPNGB_EMIT(px >> 16); }
+            }
+        }
+    }
+    for (uint32_t i = 0; i < nacc; i++) rowp[dcol - nacc + i] = (uint8_t)(acc >> (8u * i));
+#undef FPNGB_EMIT
+#undef FPNGB_LITERAL
+}
+
 // "keep the last 4 literal bytes" monoid: a then b  (v holds the last n literals, most recent in the top byte)
 __device__ __forceinline__ void lit_combine(uint32_t& n, uint32_t& v, uint32_t nb, uint32_t vb)
 {
@@ -612,9 +687,11 @@ __global__ void __launch_bounds__(kDecThreads) decode_write_kernel(DecodeParams 
     const uint32_t chans = p.chans, bpl = p.w * chans, h = p.h, pitch = p.delta_pitch;
     uint32_t err = 0;
     const unsigned long long hi_abs = (g + 1) * kSubBits;
-    if (in.start < hi_abs)
-        decode_range<true>(sm, s_lut, in.start, 0u, 0u, (uint32_t)(hi_abs - in.start), chans, p.delta + (size_t)f * pitch * h, pitch, bpl, h,
-                           in.exit /*out_pos*/, in.lits /*tail*/, &err);
+    if (in.start < hi_abs) {
+        uint8_t* dl = p.delta + (size_t)f * pitch * h;
+        if (chans == 4) decode_write_range<4>(sm, s_lut, in.start, (uint32_t)(hi_abs - in.start), dl, pitch, bpl, h, in.exit /*out_pos*/, in.lits /*tail*/, &err);
+        else decode_write_range<3>(sm, s_lut, in.start, (uint32_t)(hi_abs - in.start), dl, pitch, bpl, h, in.exit /*out_pos*/, in.lits /*tail*/, &err);
+    }
     if (err) stp->status = 1;
 }
 
