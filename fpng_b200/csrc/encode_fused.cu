@@ -104,23 +104,38 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
     asm volatile("st.volatile.global.u64 [%0], %1;\n" :: "l"(p), "l"(v) : "memory");
 }
 
-// Lane-local bit string: branch-free append (the slot is private, so the word in progress can be stored on every put).
+// Lane-local bit string: the slot is private, so the word in progress can be stored on every put.  P is the running bit
+// count; shifts use it modulo 32 (funnel shifts wrap), a put crosses into the next word iff bit 5 of P changes (len < 32).
 struct LaneStager {
-    uint32_t cur, n, dst, base;
-    __device__ __forceinline__ void begin(uint32_t slot_saddr) { cur = 0u; n = 0u; dst = slot_saddr; base = slot_saddr; }
-    __device__ __forceinline__ void put(uint32_t code, uint32_t len)          // len <= 32 - ... codes here are <= 24 bits
+    uint32_t cur, P, dst;
+    __device__ __forceinline__ void begin(uint32_t slot_saddr) { cur = 0u; P = 0u; dst = slot_saddr; }
+    __device__ __forceinline__ void put(uint32_t code, uint32_t len)          // len < 32, code < 2^len
     {
-        const uint32_t lo = cur | (code << n);
-        const uint32_t hi = __funnelshift_l(code, 0u, n);                    // bits spilling into the next word (0 when n == 0)
-        const uint32_t n2 = n + len;
+        const uint32_t lo = cur | __funnelshift_l(0u, code, P);             // code << (P & 31)
+        const uint32_t hi = __funnelshift_l(code, 0u, P);                    // bits spilling into the next word (0 when P & 31 == 0)
+        const uint32_t P2 = P + len;
         sts32(dst, lo);
-        const uint32_t adv = n2 >> 5;
-        dst += adv << 2;
-        cur = adv ? hi : lo;
-        n = n2 & 31u;
+        if ((P ^ P2) & 32u) { dst += 4u; cur = hi; } else cur = lo;
+        P = P2;
     }
-    __device__ __forceinline__ uint32_t finish() { sts32(dst, cur); return ((dst - base) << 3) + n; }
+    __device__ __forceinline__ uint32_t finish() { sts32(dst, cur); return P; }
 };
+
+// FPNGB_LIT64: literal table entries as (code, size) register pairs fetched with one 64-bit shared load, instead of one
+// packed 32-bit word whose fields have to be shifted / masked apart (2 ALU instructions less per literal)
+#ifndef FPNGB_LIT64
+#define FPNGB_LIT64 1
+#endif
+#if FPNGB_LIT64
+__device__ __forceinline__ uint2 lds64c(uint32_t saddr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(saddr)); return v; }
+template <int POS>
+__device__ __forceinline__ uint32_t flit_off8(uint32_t w, uint32_t nb)
+{
+    const uint32_t x = POS == 0 ? (w << 3) : (POS == 1 ? (w >> 5) : (POS == 2 ? (w >> 13) : (w >> 21)));
+    return (x & 0x7F8u) | nb;
+}
+__device__ __forceinline__ void fput_pair2(LaneStager& bs, uint2 a, uint2 b) { bs.put(a.x | (b.x << a.y), a.y + b.y); }
+#endif
 
 __device__ __forceinline__ void fput_pair(LaneStager& bs, uint32_t a, uint32_t b)
 {
@@ -140,11 +155,39 @@ __device__ __forceinline__ uint32_t flit_off(uint32_t w, uint32_t nb)
 }
 __device__ __forceinline__ void fput_word(LaneStager& bs, uint32_t lit_s, uint32_t w, uint32_t nb)
 {
+#if FPNGB_LIT64
+    const uint32_t nb8 = nb << 1;                                            // null half of the 8-byte table
+    const uint32_t l64 = lit_s - 4096u;                                       // the 8-byte table sits directly below the 4-byte one
+    const uint2 e0 = lds64c(l64 + flit_off8<0>(w, nb8)), e1 = lds64c(l64 + flit_off8<1>(w, nb8));
+    const uint2 e2 = lds64c(l64 + flit_off8<2>(w, nb8)), e3 = lds64c(l64 + flit_off8<3>(w, nb8));
+    fput_pair2(bs, e0, e1);
+    fput_pair2(bs, e2, e3);
+#else
     const uint32_t e0 = lds32c(lit_s + flit_off<0>(w, nb)), e1 = lds32c(lit_s + flit_off<1>(w, nb));
     const uint32_t e2 = lds32c(lit_s + flit_off<2>(w, nb)), e3 = lds32c(lit_s + flit_off<3>(w, nb));
     fput_pair(bs, e0, e1);
     fput_pair(bs, e2, e3);
+#endif
 }
+// the 4 literal codes of a word whose bytes belong to two pixels: bytes [0, SPLIT) carry null flag nbA, bytes [SPLIT, 4) nbB
+// (0 or 0x400: the all-zero half of the table switches a pixel's literals off without a branch)
+template <int SPLIT>
+__device__ __forceinline__ void fput_word_2nb(LaneStager& bs, uint32_t lit_s, uint32_t w, uint32_t nbA, uint32_t nbB)
+{
+#if FPNGB_LIT64
+    const uint32_t l64 = lit_s - 4096u, a8 = nbA << 1, b8 = nbB << 1;
+    const uint2 e0 = lds64c(l64 + flit_off8<0>(w, SPLIT > 0 ? a8 : b8)), e1 = lds64c(l64 + flit_off8<1>(w, SPLIT > 1 ? a8 : b8));
+    const uint2 e2 = lds64c(l64 + flit_off8<2>(w, SPLIT > 2 ? a8 : b8)), e3 = lds64c(l64 + flit_off8<3>(w, SPLIT > 3 ? a8 : b8));
+    fput_pair2(bs, e0, e1);
+    fput_pair2(bs, e2, e3);
+#else
+    const uint32_t e0 = lds32c(lit_s + flit_off<0>(w, SPLIT > 0 ? nbA : nbB)), e1 = lds32c(lit_s + flit_off<1>(w, SPLIT > 1 ? nbA : nbB));
+    const uint32_t e2 = lds32c(lit_s + flit_off<2>(w, SPLIT > 2 ? nbA : nbB)), e3 = lds32c(lit_s + flit_off<3>(w, SPLIT > 3 ? nbA : nbB));
+    fput_pair(bs, e0, e1);
+    fput_pair(bs, e2, e3);
+#endif
+}
+
 template <int CHANS>
 __device__ __forceinline__ void fput_literal(LaneStager& bs, uint32_t lit_s, uint32_t px)
 {
@@ -192,7 +235,12 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
     const uint32_t nwarps = blockDim.x >> 5;
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(dyn_smem + kFusedWarps * kUnitBytes);
     const uint32_t stage_words = kFusedWarps * kUnitWords + 2;
+#if FPNGB_LIT64
+    uint32_t* s_lit64 = s_stage + stage_words;      // [512][2]: (code, size) pairs + the all-zero null half, directly below s_lit
+    uint32_t* s_lit = s_lit64 + 1024;
+#else
     uint32_t* s_lit = s_stage + stage_words;
+#endif
     uint32_t* s_match = s_lit + 512;
     uint32_t* s_small = s_match + 88;               // 48 words
     // s_small: [0..7] has_lit, [8..15] trail, [16..23] npix, [24..31] unit bits, [32] ticket, [33] pred tail, [34] sh, [35] status
@@ -206,7 +254,13 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
     const uint32_t img = ticket / p.groups_per_image, g = ticket - img * p.groups_per_image;
     if (img >= p.n_images) return;
     const CodeBook* book = p.books + (size_t)img * p.book_stride;
-    for (uint32_t i = tid; i < 256; i += blockDim.x) { s_lit[i] = book->lit[i]; s_lit[256 + i] = 0u; }
+    for (uint32_t i = tid; i < 256; i += blockDim.x) {
+        const uint32_t e = book->lit[i];
+        s_lit[i] = e; s_lit[256 + i] = 0u;
+#if FPNGB_LIT64
+        s_lit64[2 * i] = e & 0xFFFFu; s_lit64[2 * i + 1] = e >> 16; s_lit64[512 + 2 * i] = 0u; s_lit64[512 + 2 * i + 1] = 0u;
+#endif
+    }
     if (tid < 88) s_match[tid] = book->match[tid];
     uint32_t* s_crc = reinterpret_cast<uint32_t*>(s_u64 + 18);                // [4][256] slice tables of the 128-byte advance
     if (p.inline_crc) for (uint32_t i = tid; i < 1024; i += blockDim.x) s_crc[i] = (&g_f128b[0][0])[i];
@@ -305,31 +359,45 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
                 if (ev8) fput_match(bs, match_s, M);
             } else if (__reduce_add_sync(kFullMask, (uint32_t)__popc(lit8)) >= 16u) {
                 const uint32_t nl = ~lit8;
+                if (CHANS == 4) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    if (ev8 & (1u << k)) {
-                        const uint32_t kk = 8u * hh + k;
-                        const uint32_t len = ((eqm >> kk) & 1u) ? M : frun_before<M>(eqm, r_lane, kk);
-                        if (len) fput_match(bs, match_s, len);
-                    }
-                    const uint32_t nb = (k <= 10 ? (nl << (10 - k)) : (nl >> (k - 10))) & 0x400u;
-                    if (CHANS == 4) fput_word(bs, lit_s, hw[k % kHalfWords], nb);
-                    else {
-                        // bytes 3k .. 3k+2 of the half's 24 filtered bytes
-                        uint32_t e0, e1, e2;
-                        switch (k) {
-                        default:
-                        case 0: e0 = lds32c(lit_s + flit_off<0>(hw[0], nb)); e1 = lds32c(lit_s + flit_off<1>(hw[0], nb)); e2 = lds32c(lit_s + flit_off<2>(hw[0], nb)); break;
-                        case 1: e0 = lds32c(lit_s + flit_off<3>(hw[0], nb)); e1 = lds32c(lit_s + flit_off<0>(hw[1], nb)); e2 = lds32c(lit_s + flit_off<1>(hw[1], nb)); break;
-                        case 2: e0 = lds32c(lit_s + flit_off<2>(hw[1], nb)); e1 = lds32c(lit_s + flit_off<3>(hw[1], nb)); e2 = lds32c(lit_s + flit_off<0>(hw[2], nb)); break;
-                        case 3: e0 = lds32c(lit_s + flit_off<1>(hw[2], nb)); e1 = lds32c(lit_s + flit_off<2>(hw[2], nb)); e2 = lds32c(lit_s + flit_off<3>(hw[2], nb)); break;
-                        case 4: e0 = lds32c(lit_s + flit_off<0>(hw[3 % kHalfWords], nb)); e1 = lds32c(lit_s + flit_off<1>(hw[3 % kHalfWords], nb)); e2 = lds32c(lit_s + flit_off<2>(hw[3 % kHalfWords], nb)); break;
-                        case 5: e0 = lds32c(lit_s + flit_off<3>(hw[3 % kHalfWords], nb)); e1 = lds32c(lit_s + flit_off<0>(hw[4 % kHalfWords], nb)); e2 = lds32c(lit_s + flit_off<1>(hw[4 % kHalfWords], nb)); break;
-                        case 6: e0 = lds32c(lit_s + flit_off<2>(hw[4 % kHalfWords], nb)); e1 = lds32c(lit_s + flit_off<3>(hw[4 % kHalfWords], nb)); e2 = lds32c(lit_s + flit_off<0>(hw[5 % kHalfWords], nb)); break;
-                        case 7: e0 = lds32c(lit_s + flit_off<1>(hw[5 % kHalfWords], nb)); e1 = lds32c(lit_s + flit_off<2>(hw[5 % kHalfWords], nb)); e2 = lds32c(lit_s + flit_off<3>(hw[5 % kHalfWords], nb)); break;
+                    for (int k = 0; k < 8; k++) {
+                        if (ev8 & (1u << k)) {
+                            const uint32_t kk = 8u * hh + k;
+                            const uint32_t len = ((eqm >> kk) & 1u) ? M : frun_before<M>(eqm, r_lane, kk);
+                            if (len) fput_match(bs, match_s, len);
                         }
-                        fput_pair(bs, e0, e1);
-                        bs.put(e2 & 0xFFFFu, e2 >> 16);
+                        const uint32_t nb = (k <= 10 ? (nl << (10 - k)) : (nl >> (k - 10))) & 0x400u;
+                        fput_word(bs, lit_s, hw[k % kHalfWords], nb);
+                    }
+                } else {
+                    // RGB: the half's 24 filtered bytes as 6 words; word j holds bytes of pixels (4j)/3 .. (4j+3)/3.  A pixel's
+                    // literals are switched off through the table's null half; the rare run tokens (at most a few per warp
+                    // step) are inserted by a byte-wise emission of the one word in which the token's pixel starts.
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        constexpr int kFirstPx[6] = {0, 1, 2, 4, 5, 6};     // pixel of the word's first byte
+                        constexpr int kSplit[6] = {3, 2, 1, 3, 2, 1};       // bytes of that pixel inside the word
+                        constexpr uint32_t kStarts[6] = {0x03u, 0x04u, 0x08u, 0x30u, 0x40u, 0x80u};   // pixels whose first byte lies in the word
+                        const int pa = kFirstPx[j];
+                        const uint32_t wj = hw[j % kHalfWords];
+                        if (ev8 & kStarts[j]) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const int bidx = 4 * j + i, px = bidx / 3;
+                                if (bidx % 3 == 0 && (ev8 & (1u << px))) {
+                                    const uint32_t kk = 8u * hh + px;
+                                    const uint32_t len = ((eqm >> kk) & 1u) ? M : frun_before<M>(eqm, r_lane, kk);
+                                    if (len) fput_match(bs, match_s, len);
+                                }
+                                if (lit8 & (1u << px)) { const uint32_t e = lds32c(lit_s + (((wj >> (8 * i)) & 0xFFu) << 2)); bs.put(e & 0xFFFFu, e >> 16); }
+                            }
+                        } else {
+                            const uint32_t nbA = (nl << (10 - pa)) & 0x400u, nbB = (nl << (10 - (pa + 1))) & 0x400u;
+                            if (kSplit[j] == 3) fput_word_2nb<3>(bs, lit_s, wj, nbA, nbB);
+                            else if (kSplit[j] == 2) fput_word_2nb<2>(bs, lit_s, wj, nbA, nbB);
+                            else fput_word_2nb<1>(bs, lit_s, wj, nbA, nbB);
+                        }
                     }
                 }
             } else {
@@ -684,7 +752,7 @@ void launch_fused_crc(const void* desc_mem, uint32_t n, uint32_t w, uint32_t h, 
 // ------------------------------------------------------------------------------------------------------------------
 template <int CHANS, bool DIRECT> constexpr size_t fused_smem()
 {
-    return (size_t)kFusedWarps * fused_unit_bytes<CHANS, DIRECT>() + ((size_t)kFusedWarps * fused_unit_words<CHANS>() + 2 + 512 + 88 + 48) * 4 + 18 * 8 + 1024 * 4 + 16;
+    return (size_t)kFusedWarps * fused_unit_bytes<CHANS, DIRECT>() + ((size_t)kFusedWarps * fused_unit_words<CHANS>() + 2 + 512 + 88 + 48 + (FPNGB_LIT64 ? 1024 : 0)) * 4 + 18 * 8 + 1024 * 4 + 16;
 }
 
 bool fused_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t h, uint32_t chans, uint32_t n)
