@@ -34,6 +34,8 @@ WORKLOADS = {
     "c2": dict(name="C2 256 x 1920x1080 RGB, 1-pass", w=1920, h=1080, chans=3, images=256, flags=0),
     "c3": dict(name="C3 128/GPU x 3840x2160 RGBA (green->alpha), 1-pass", w=3840, h=2160, chans=4, images=128, flags=0),
     "c4": dict(name="C4 128/GPU x 2048x2048 RGB, 2-pass (FPNG_ENCODE_SLOWER)", w=2048, h=2048, chans=3, images=128, flags=1),
+    # not a BASELINE config: the reference's own test image shape (example.png, 687 x 1012 RGB): 2061-byte scanlines, no alignment at all
+    "odd": dict(name="ODD 512 x 687x1012 RGB (unaligned 2061-byte scanlines), 1-pass", w=687, h=1012, chans=3, images=512, flags=0),
 }
 N_UNIQUE_NOISE = 16
 
@@ -287,6 +289,9 @@ def run_ours(args, wl):
     L = lib()
     # multi-rank runs: keep this rank's host threads and pinned staging on the GPU's own NUMA node (e2e legs are PCIe-bound)
     numa_node = L.fpngb_bind_host_thread_to_device_numa() if world > 1 else -1
+    if args.encoder != "default":
+        L.fpngb_debug_use_fused(1 if args.encoder == "fused" else 0)
+        L.fpngb_debug_crc_overlap(1 if args.encoder == "two_kernel" else 0)
     L.fpngb_profile_enable.argtypes = [C.c_int]
     L.fpngb_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int]
 
@@ -383,7 +388,9 @@ def run_ours(args, wl):
                    "g1_noise": "gradient + uniform integer noise in [-3, 3] from numpy RandomState(1234 + i % 16).randint (MT19937; SURVEY 8d words it as std::mt19937(1234 + i): same engine, different integer mapping, 16 distinct noise fields per batch); both arms use this generator"},
         "clocks": clocks, "gpu_launches": int(launches),
         "kernels_ms": kern, "roofline": roof(dominant), "roofline_scan": roof("fused" if fused_path else "scan"),
-        "encoder": "single-pass fused kernel (encode_fused.cu: filter + match + code emission + bit placement in one read of the pixels)" if fused_path else "two-kernel scan + pack",
+        "encoder": "single-pass fused kernel (encode_fused.cu: filter + match + code emission + bit placement in one read of the pixels)" if fused_path
+                   else "two-kernel scan + pack",
+        "kernels_ms_sum": float(sum(kern.values())),
         "whole_step": {"algorithmic_gbs": (in_bytes + out_bytes) / 1e9 / (ms / args.steps / 1e3),
                        "frac_of_peak": (in_bytes + out_bytes) / 1e9 / (ms / args.steps / 1e3) / peak},
     }
@@ -621,6 +628,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--encoder", default="default", choices=["default", "two_kernel", "two_kernel_serial", "fused"],
+                    help="default: the library's choice; two_kernel: scan+pack with the chunked CRC overlap; two_kernel_serial: scan+pack, serial; fused: single-pass encoder")
     ap.add_argument("--own-files", action="store_true", help="decode leg: use the GPU-written files instead of reference-written ones")
     args = ap.parse_args()
     if args.workload == "auto":

@@ -84,6 +84,14 @@ def lib() -> C.CDLL:
                                               C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     L.fpngb_bind_host_thread_to_device_numa.restype = C.c_int
     L.fpngb_launch_count.restype = C.c_uint64
+    L.fpngb_debug_use_fused.restype = None
+    L.fpngb_debug_use_fused.argtypes = [C.c_int]
+    L.fpngb_debug_crc_overlap.restype = None
+    L.fpngb_debug_crc_overlap.argtypes = [C.c_int]
+    L.fpngb_debug_crc_stream.restype = None
+    L.fpngb_debug_crc_stream.argtypes = [C.c_int]
+    L.fpngb_debug_inline_crc.restype = None
+    L.fpngb_debug_inline_crc.argtypes = [C.c_int]
     L.fpngb_debug_rows_per_warp.restype = None
     L.fpngb_debug_rows_per_warp.argtypes = [C.c_uint32]
     L.fpngb_debug_static_table.restype = C.c_int

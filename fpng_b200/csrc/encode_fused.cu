@@ -126,6 +126,9 @@ struct LaneStager {
 #ifndef FPNGB_LIT64
 #define FPNGB_LIT64 1
 #endif
+#ifndef FPNGB_FUSED_TICKET
+#define FPNGB_FUSED_TICKET 0
+#endif
 #if FPNGB_LIT64
 __device__ __forceinline__ uint2 lds64c(uint32_t saddr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(saddr)); return v; }
 template <int POS>
@@ -247,10 +250,18 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
     unsigned long long* s_u64 = reinterpret_cast<unsigned long long*>(s_small + 48);     // [0..7] adler A, [8..15] adler B, [16] base (file bit of the group's first bit)
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    // Row groups are processed in stream order.  CTAs of a 1-D grid are dispatched in blockIdx order on every NVIDIA GPU (the
+    // decoupled look-back of CUB's device-wide scan relies on the same property), so a group only waits for groups that are
+    // already resident; FPNGB_FUSED_TICKET=1 (build flag) switches to an atomic ticket, which does not depend on that.
+#if FPNGB_FUSED_TICKET
     if (tid == 0) s_small[32] = atomicAdd(p.ticket, 1u);
     for (uint32_t i = tid; i < stage_words; i += blockDim.x) s_stage[i] = 0u;
     __syncthreads();
     const uint32_t ticket = s_small[32];
+#else
+    for (uint32_t i = tid; i < stage_words; i += blockDim.x) s_stage[i] = 0u;
+    const uint32_t ticket = blockIdx.x;
+#endif
     const uint32_t img = ticket / p.groups_per_image, g = ticket - img * p.groups_per_image;
     if (img >= p.n_images) return;
     const CodeBook* book = p.books + (size_t)img * p.book_stride;
@@ -490,9 +501,11 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
             else if (outw) red_or32(stage_s + k * 4u, outw);
         }
     }
+    __syncthreads();                                                         // #3: staging complete
+    const uint32_t NWc = (group_bits + 31u) >> 5;
     if (warp == 0) {
-        // decoupled look-back (single-pass chained scan), after this warp's own copy so that the wait overlaps useful work:
-        // sum the aggregates of the groups before, stop at the first group that already knows its inclusive end position
+        // decoupled look-back (single-pass chained scan) while the other warps compute the CRC partial: sum the aggregates of
+        // the groups before, stop at the first group that already knows its inclusive end position
         unsigned long long base = 0;
         uint32_t status = 0;
         if (g == 0) {
@@ -511,6 +524,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
                 const uint32_t needed = first >= 31u ? kFullMask : ((2u << first) - 1u);   // lanes whose value enters the sum
                 if (empty & needed) {                                       // a predecessor that matters has not published yet: look again
                     if (++spins > kSpinLimit) { status = 1u; break; }
+                    __nanosleep(200);                                       // leave the issue slots to the CTAs that still have work
                     continue;
                 }
                 unsigned long long contrib = (lane <= first && idx >= 0) ? (v & kValueMask) : 0ull;
@@ -526,22 +540,43 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
             st_volatile_u64(&desc[g].agg, ((unsigned long long)kStateIncl << 62) | end);
             s_u64[16] = base;
             s_small[35] = status;
+            // the word shared with the predecessor / successor.  This group's own trailing partial word (bits below span & 31
+            // of word nfull) does not depend on the predecessor when the group completes at least one word (always, except
+            // for degenerate tiny groups): it is published BEFORE waiting for the predecessor's, so the tails of consecutive
+            // groups do not form a serial chain.
+            const uint32_t sh = (uint32_t)(base & 31ull);
+            const unsigned long long W0 = base >> 5;
+            const uint32_t span = sh + group_bits, nfull = span >> 5;
+            uint32_t tailw = 0;
+            if (span & 31u) tailw = __funnelshift_l(nfull ? s_stage[nfull - 1] : 0u, s_stage[nfull], sh);
+            if (nfull) st_volatile_u64(&desc[g].tail, kTailReady | tailw);
+            uint32_t pred = 0;
+            if (sh && !status) {
+                if (g == 0) {
+                    const uint32_t byte0 = (uint32_t)(W0 << 2) - kPngHeaderSize;  // always inside the block header bytes (hdr_bits > 64)
+                    const uint32_t word = (uint32_t)book->hdr[byte0] | ((uint32_t)book->hdr[byte0 + 1] << 8) | ((uint32_t)book->hdr[byte0 + 2] << 16) | ((uint32_t)book->hdr[byte0 + 3] << 24);
+                    pred = word & ((1u << sh) - 1u);
+                } else {
+                    unsigned long long t;
+                    uint32_t spins = 0;
+                    while (!((t = ld_volatile_u64(&desc[g - 1].tail)) & kTailReady) && ++spins < kSpinLimit) __nanosleep(100);
+                    if (!(t & kTailReady)) p.st[img].status = 3u;
+                    pred = (uint32_t)t;
+                }
+            }
+            s_small[33] = pred;
+            if (!nfull) st_volatile_u64(&desc[g].tail, kTailReady | tailw | pred);
         }
+        if (p.inline_crc && lane == 0 && nwarps > 1) s_small[36] = 0u;
     }
-    __syncthreads();                                                         // #3: staging complete, base known
-    const unsigned long long base = s_u64[16];
-    const uint32_t sh = (uint32_t)(base & 31ull);
-    const unsigned long long W0 = base >> 5;
-    const uint32_t span = sh + group_bits, nfull = span >> 5;                // words whose bit 31 this group covers
-    if (s_small[35]) { if (tid == 0) p.st[img].status = 2u; return; }
-
-    // ---- CRC-32 partial of the group's bit string (staging words, group-relative: independent of the file position)
-    if (p.inline_crc) {
-        const uint32_t NW = (group_bits + 31u) >> 5;
+    // ---- CRC-32 partial of the group's bit string (staging words, group-relative: independent of the file position); warp 0
+    // is busy with the look-back unless it is the only warp
+    if (p.inline_crc && (warp != 0 || nwarps == 1)) {
+        const uint32_t cw = nwarps > 1 ? nwarps - 1u : 1u, first = nwarps > 1 ? warp - 1u : 0u;
         uint32_t acc = 0;
-        // warp `warp` takes the chunks warp, warp + nwarps, ... counted from the END of the string
-        for (uint32_t m = warp; m * kCrcChunkWords < NW; m += nwarps) {
-            const int j0 = (int)NW - (int)((m + 1u) * kCrcChunkWords) + (int)lane;      // this lane's first word of the chunk (may be < 0: front padding)
+        // this warp takes the chunks first, first + cw, ... counted from the END of the string
+        for (uint32_t m = first; m * kCrcChunkWords < NWc; m += cw) {
+            const int j0 = (int)NWc - (int)((m + 1u) * kCrcChunkWords) + (int)lane;     // this lane's first word of the chunk (may be < 0: front padding)
             uint32_t c = 0;
 #pragma unroll
             for (uint32_t k = 0; k < kCrcChunkWords / 32u; k++) {
@@ -561,37 +596,17 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
         }
         if (lane == 0) s_small[36 + warp] = acc;
     }
-
-    // ---- phase 4b: the word shared with the predecessor / successor
-    if (tid == 0) {
-        // this group's own trailing partial word (bits below span & 31 of word nfull).  When the group completes at least
-        // one word (nfull >= 1: always, except for degenerate tiny groups) the tail does not depend on the predecessor and is
-        // published BEFORE waiting for the predecessor's, so the tails of consecutive groups do not form a serial chain.
-        uint32_t tailw = 0;
-        if (span & 31u) tailw = __funnelshift_l(nfull ? s_stage[nfull - 1] : 0u, s_stage[nfull], sh);
-        if (nfull) st_volatile_u64(&desc[g].tail, kTailReady | tailw);
-        uint32_t pred = 0;
-        if (sh) {
-            if (g == 0) {
-                const uint32_t byte0 = (uint32_t)(W0 << 2) - kPngHeaderSize;  // always inside the block header bytes (hdr_bits > 64)
-                const uint32_t word = (uint32_t)book->hdr[byte0] | ((uint32_t)book->hdr[byte0 + 1] << 8) | ((uint32_t)book->hdr[byte0 + 2] << 16) | ((uint32_t)book->hdr[byte0 + 3] << 24);
-                pred = word & ((1u << sh) - 1u);
-            } else {
-                unsigned long long t;
-                uint32_t spins = 0;
-                do { t = ld_volatile_u64(&desc[g - 1].tail); } while (!(t & kTailReady) && ++spins < kSpinLimit);
-                if (!(t & kTailReady)) p.st[img].status = 3u;
-                pred = (uint32_t)t;
-            }
-        }
-        s_small[33] = pred;
-        if (!nfull) st_volatile_u64(&desc[g].tail, kTailReady | tailw | pred);
-    }
-    __syncthreads();                                                         // #4: pred tail, CRC partials
+    __syncthreads();                                                         // #4: base, pred tail, CRC partials
+    const unsigned long long base = s_u64[16];
+    const uint32_t sh = (uint32_t)(base & 31ull);
+    const unsigned long long W0 = base >> 5;
+    const uint32_t span = sh + group_bits, nfull = span >> 5;                // words whose bit 31 this group covers
+    (void)span;
+    if (s_small[35]) { if (tid == 0) p.st[img].status = 2u; return; }
     if (p.inline_crc && tid == 0) {
         uint32_t r = 0;
         for (uint32_t u = 0; u < nwarps; u++) r ^= s_small[36 + u];
-        desc[g].crc = (unsigned long long)r | ((unsigned long long)((group_bits + 31u) >> 5) << 32);
+        desc[g].crc = (unsigned long long)r | ((unsigned long long)NWc << 32);
     }
     // ---- phase 4c: write the complete words, shifted to the group's position in the file
     {

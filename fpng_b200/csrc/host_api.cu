@@ -23,8 +23,11 @@
 namespace fpngb {
 
 static std::atomic<uint64_t> g_launches{0};
-static bool g_no_fused_override = false;
-static bool g_inline_crc = true;                // fpngb_debug_inline_crc(): the single-pass encoder computes the IDAT CRC from in-kernel partials       // fpngb_debug_disable_fused(): tests run both encoders in one process
+
+static bool g_inline_crc = true;                // fpngb_debug_inline_crc(): the single-pass encoder computes the IDAT CRC from in-kernel partials
+static bool g_crc_stream = true;                // fpngb_debug_crc_stream(0): first-generation (tile-staging) IDAT CRC kernel
+static int g_fused_mode = -1;                   // fpngb_debug_use_fused(): 1 single-pass encoder, 0 two-kernel encoder, -1 environment (FPNGB_FUSED)
+static bool g_crc_overlap = false;              // fpngb_debug_crc_overlap(1): chunked batches with the CRC kernel on a side stream (measured slower: profiles/README.md)
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -147,7 +150,8 @@ Context& context() { return g_ctx; }
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
 enum ProfSlot { kProfHist = 0, kProfHuff, kProfScan, kProfOffsets, kProfFused, kProfFinish, kProfPack, kProfAdler, kProfCrc, kProfSlots };
-struct ProfSet { cudaEvent_t ev[kProfSlots + 1]; bool used[kProfSlots]; };
+struct ProfSet { cudaEvent_t ev[kProfSlots + 1]; cudaEvent_t crc_start; bool used[kProfSlots]; bool crc_side; uint64_t call; };
+static uint64_t g_prof_call = 0;                // encode calls seen while profiling (a chunked call owns several ProfSets)
 static bool g_profile = false;
 static std::vector<ProfSet*> g_prof_sets;      // one per encode call since the last read
 static std::vector<ProfSet*> g_prof_free;
@@ -160,7 +164,9 @@ static ProfSet* prof_begin(cudaStream_t s)
     else {
         ps = new ProfSet();
         for (int i = 0; i <= kProfSlots; i++) if (cudaEventCreate(&ps->ev[i]) != cudaSuccess) { delete ps; return nullptr; }
+        if (cudaEventCreate(&ps->crc_start) != cudaSuccess) { delete ps; return nullptr; }
     }
+    ps->crc_side = false; ps->call = g_prof_call;
     for (int i = 0; i < kProfSlots; i++) ps->used[i] = false;
     cudaEventRecord(ps->ev[0], s);
     g_prof_sets.push_back(ps);
@@ -244,6 +250,15 @@ static void make_png_header(uint8_t* hdr, uint32_t w, uint32_t h, uint32_t chans
 }
 
 // Enqueue the whole encode pipeline for a device-resident batch.  Caller holds ctx.mu.
+//
+// Two encoders share this entry:
+//  * the two-kernel encoder (scan -> offsets -> pack -> adler -> crc), the default.  Optionally (fpngb_debug_crc_overlap) large
+//    batches are cut into chunks and the CRC kernel of chunk k runs on a side stream underneath the scan and pack kernels of
+//    chunk k + 1 -- measured SLOWER on B200 (C2: 2.79 vs 2.60 ms: the kernels slow each other down more than the overlap
+//    gains), so it is off by default;
+//  * the single-pass encoder (encode_fused.cu), selected with FPNGB_FUSED=1 / fpngb_debug_use_fused(1): reads the pixels once
+//    and writes the file once, byte-identical output, measured slower on B200 (profiles/README.md) because the path is bound by
+//    instruction issue, not by HBM.
 static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image_stride, uint32_t n, uint32_t w, uint32_t h,
                                uint32_t chans, uint32_t flags, uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, cudaStream_t s)
 {
@@ -251,13 +266,13 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     // second-generation kernels (16 pixels per lane, coalesced 128-bit loads) whenever every scanline is 16-byte aligned;
     // FPNGB_FORCE_GENERIC=1 keeps the generic kernels (tests compare both)
     static const bool force_generic = getenv("FPNGB_FORCE_GENERIC") && atoi(getenv("FPNGB_FORCE_GENERIC")) != 0;
-    static const bool no_fused = getenv("FPNGB_NO_FUSED") && atoi(getenv("FPNGB_NO_FUSED")) != 0;
+    static const bool env_fused = getenv("FPNGB_FUSED") && atoi(getenv("FPNGB_FUSED")) != 0;
     // RGBA 1-pass under a table where a one-pixel match can lose against four literals: only the generic kernels
     // implement the reference's check (fpng.cpp:1520-1528); it cannot fire with the shipped table
     const uint32_t lit1_rule = (!two_pass && chans == 4 && c.h_static_books[1].lit1_rule) ? 1u : 0u;
     const bool v2 = !force_generic && !lit1_rule && walk16_eligible(d_pixels, image_stride, w, chans);
-    // third generation: single pass over the pixels (encode_fused.cu) for every shape it covers (w <= 4096, aligned scanlines)
-    const bool fused = !force_generic && !lit1_rule && !no_fused && !g_no_fused_override && !(flags & FPNGB_FORCE_UNCOMPRESSED) &&
+    const bool want_fused = g_fused_mode == 1 || (g_fused_mode < 0 && env_fused);
+    const bool fused = want_fused && !force_generic && !lit1_rule && !(flags & FPNGB_FORCE_UNCOMPRESSED) &&
                        fused_eligible(d_pixels, image_stride, w, h, chans, n);
     Workspace ws;
     int rc = carve_workspace(c, n, h, w, two_pass, ws, fused);
@@ -265,75 +280,101 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     rc = c.ws_acquire(s);
     if (rc) return rc;
     const int mode = pick_load_mode(d_pixels, image_stride, w, chans);
-    const CodeBook* books = two_pass ? ws.books : c.d_static_books + (chans == 4 ? 1 : 0);
+    const CodeBook* books0 = two_pass ? ws.books : c.d_static_books + (chans == 4 ? 1 : 0);
     const uint32_t book_stride = two_pass ? 1u : 0u;
+    const uint32_t merge_first_unit = (!two_pass && chans == 3) ? 1u : 0u;
+    uint8_t png_header[kPngHeaderSize];
+    make_png_header(png_header, w, h, chans);
+    if (g_profile) g_prof_call++;
 
-    ScanParams sp{};
-    sp.pixels = d_pixels; sp.image_stride = image_stride; sp.w = w; sp.h = h;
-    sp.books = books; sp.book_stride = book_stride;
-    sp.row_bits = ws.row_bits; sp.row_adler = ws.row_adler; sp.st = ws.st; sp.hist = ws.hist;
-    sp.merge_first_unit = (!two_pass && chans == 3) ? 1u : 0u;
-    sp.lane_ofs = ws.lane_ofs; sp.lane_ofs_pitch = ws.lane_ofs_pitch;
-    sp.lit1_rule = lit1_rule;
+    // chunks: the CRC of one chunk overlaps the scan/pack of the next.  Small batches (and the single-pass encoder) run as one chunk.
+    const uint32_t nchunks = (!fused && g_crc_overlap && n >= 16) ? 4u : 1u;
+    if (nchunks > 1) {
+        if (!c.side) FPNGB_CUDA_OK(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+        for (int i = 0; i < 5; i++) if (!c.side_ev[i]) FPNGB_CUDA_OK(cudaEventCreateWithFlags(&c.side_ev[i], cudaEventDisableTiming));
+    }
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t i0 = (uint32_t)((uint64_t)n * k / nchunks), i1 = (uint32_t)((uint64_t)n * (k + 1) / nchunks), cnt = i1 - i0;
+        if (!cnt) continue;
+        const uint8_t* px = d_pixels + (size_t)i0 * image_stride;
+        uint8_t* out = d_out + (size_t)i0 * out_stride;
+        const CodeBook* books = books0 + (size_t)i0 * book_stride;
+        const size_t r0 = (size_t)i0 * h;
 
-    ProfSet* ps = prof_begin(s);
-    if (two_pass) {
-        FPNGB_CUDA_OK(cudaMemsetAsync(ws.hist, 0, (size_t)n * 288 * 4, s));
-        if (v2) launch_hist16(sp, n, chans, s); else launch_scan(sp, n, chans, mode, true, s);
-        prof_mark(ps, kProfHist, s);
-        HuffParams hp{ws.hist, ws.books, chans, 0u};
-        launch_huffman_build(hp, n, s);
-        prof_mark(ps, kProfHuff, s);
+        ScanParams sp{};
+        sp.pixels = px; sp.image_stride = image_stride; sp.w = w; sp.h = h;
+        sp.books = books; sp.book_stride = book_stride;
+        sp.row_bits = ws.row_bits + r0; sp.row_adler = ws.row_adler + r0; sp.st = ws.st + i0; sp.hist = ws.hist + (size_t)i0 * 288;
+        sp.merge_first_unit = merge_first_unit;
+        sp.lane_ofs = ws.lane_ofs + r0 * ws.lane_ofs_pitch; sp.lane_ofs_pitch = ws.lane_ofs_pitch;
+        sp.lit1_rule = lit1_rule;
+
+        ProfSet* ps = prof_begin(s);
+        if (two_pass) {
+            FPNGB_CUDA_OK(cudaMemsetAsync(sp.hist, 0, (size_t)cnt * 288 * 4, s));
+            if (v2) launch_hist16(sp, cnt, chans, s); else launch_scan(sp, cnt, chans, mode, true, s);
+            prof_mark(ps, kProfHist, s);
+            HuffParams hp{sp.hist, ws.books + i0, chans, 0u};
+            launch_huffman_build(hp, cnt, s);
+            prof_mark(ps, kProfHuff, s);
+            count_launch(2);
+        }
+        PackParams pp{};
+        pp.pixels = px; pp.image_stride = image_stride; pp.w = w; pp.h = h; pp.books = books; pp.book_stride = book_stride;
+        pp.row_ofs = ws.row_ofs + r0; pp.row_bits = sp.row_bits; pp.lane_ofs = sp.lane_ofs; pp.lane_ofs_pitch = ws.lane_ofs_pitch;
+        pp.row_adler = sp.row_adler; pp.st = sp.st; pp.out = out; pp.out_stride = out_stride;
+        pp.lit1_rule = lit1_rule;
+        if (fused) {
+            cudaEvent_t mid = ps ? ps->ev[kProfFused + 1] : nullptr;
+            rc = launch_encode_fused(px, image_stride, cnt, w, h, chans, flags, books, book_stride, sp.row_adler, sp.st, ws.fused_desc,
+                                     out, out_stride, d_sizes + i0, png_header, merge_first_unit, s, mid, g_inline_crc);
+            if (rc) return rc;
+            if (ps) ps->used[kProfFused] = true;
+            prof_mark(ps, kProfFinish, s);
+            pp.stored_only = 1u;
+            launch_pack16(pp, cnt, chans, s);                                   // stored-block images only (fpng.cpp:1728-1758)
+            prof_mark(ps, kProfPack, s);
+            count_launch(3);
+        } else {
+            if (v2) launch_scan16(sp, cnt, chans, s); else launch_scan(sp, cnt, chans, mode, false, s);
+            prof_mark(ps, kProfScan, s);
+            OffsetsParams op{};
+            op.row_bits = sp.row_bits; op.row_ofs = ws.row_ofs + r0; op.books = books; op.book_stride = book_stride; op.st = sp.st;
+            op.out = out; op.out_stride = out_stride; op.sizes = d_sizes + i0; op.w = w; op.h = h; op.chans = chans; op.flags = flags;
+            memcpy(op.png_header, png_header, kPngHeaderSize);
+            launch_offsets(op, cnt, s);
+            prof_mark(ps, kProfOffsets, s);
+            if (v2) launch_pack16(pp, cnt, chans, s); else launch_pack(pp, cnt, chans, mode, s);
+            prof_mark(ps, kProfPack, s);
+            count_launch(3);
+        }
+        AdlerParams ap{sp.row_adler, sp.st, out, out_stride, w, h, chans};
+        launch_adler_finalize(ap, cnt, s);
+        prof_mark(ps, kProfAdler, s);
+
+        CrcParams cp{};
+        cp.out = out; cp.out_stride = out_stride; cp.st = sp.st;
+        cp.max_tiles = crc_ctas_for(max_encoded_size(w, h, chans)); cp.msg_start = kPngHeaderSize - 4; cp.init_xor = 0xFFFFFFFFu;
+        cudaStream_t cs = s;
+        if (nchunks > 1) {                                                    // this chunk's CRC goes to the side stream
+            FPNGB_CUDA_OK(cudaEventRecord(c.side_ev[k], s));
+            FPNGB_CUDA_OK(cudaStreamWaitEvent(c.side, c.side_ev[k], 0));
+            cs = c.side;
+            if (ps) { cudaEventRecord(ps->crc_start, cs); ps->crc_side = true; }
+        }
+        if (fused && g_inline_crc) {
+            launch_fused_crc(ws.fused_desc, cnt, w, h, books, book_stride, sp.st, out, out_stride, cs);   // combine the in-kernel partials
+            cp.stored_only = 1u;                                              // the file-reading CRC kernel is only needed for stored-block images
+            count_launch(1);
+        }
+        if (g_crc_stream) launch_crc_stream(cp, cnt, max_encoded_size(w, h, chans), cs); else launch_crc(cp, cnt, cs);
+        prof_mark(ps, kProfCrc, cs);
         count_launch(2);
     }
-    PackParams pp{};
-    pp.pixels = d_pixels; pp.image_stride = image_stride; pp.w = w; pp.h = h; pp.books = books; pp.book_stride = book_stride;
-    pp.row_ofs = ws.row_ofs; pp.row_bits = ws.row_bits; pp.lane_ofs = ws.lane_ofs; pp.lane_ofs_pitch = ws.lane_ofs_pitch; pp.row_adler = ws.row_adler; pp.st = ws.st; pp.out = d_out; pp.out_stride = out_stride;
-    pp.lit1_rule = lit1_rule;
-    if (fused) {
-        uint8_t png_header[kPngHeaderSize];
-        make_png_header(png_header, w, h, chans);
-        cudaEvent_t mid = ps ? ps->ev[kProfFused + 1] : nullptr;
-        rc = launch_encode_fused(d_pixels, image_stride, n, w, h, chans, flags, books, book_stride, ws.row_adler, ws.st, ws.fused_desc,
-                                 d_out, out_stride, d_sizes, png_header, sp.merge_first_unit, s, mid, g_inline_crc);
-        if (rc) return rc;
-        if (ps) ps->used[kProfFused] = true;
-        prof_mark(ps, kProfFinish, s);
-        pp.stored_only = 1u;
-        launch_pack16(pp, n, chans, s);                                     // stored-block images only (fpng.cpp:1728-1758)
-        prof_mark(ps, kProfPack, s);
-        count_launch(1);                                                    // + the 4 counted below = fused, finish, pack, adler, crc
-    } else {
-    if (v2) launch_scan16(sp, n, chans, s); else launch_scan(sp, n, chans, mode, false, s);
-    prof_mark(ps, kProfScan, s);
-
-    OffsetsParams op{};
-    op.row_bits = ws.row_bits; op.row_ofs = ws.row_ofs; op.books = books; op.book_stride = book_stride; op.st = ws.st;
-    op.out = d_out; op.out_stride = out_stride; op.sizes = d_sizes; op.w = w; op.h = h; op.chans = chans; op.flags = flags;
-    make_png_header(op.png_header, w, h, chans);
-    launch_offsets(op, n, s);
-    prof_mark(ps, kProfOffsets, s);
-
-    if (v2) launch_pack16(pp, n, chans, s); else launch_pack(pp, n, chans, mode, s);
-    prof_mark(ps, kProfPack, s);
-    count_launch(1);
+    if (nchunks > 1) {                                                        // join: the caller's stream continues after the last CRC
+        FPNGB_CUDA_OK(cudaEventRecord(c.side_ev[4], c.side));
+        FPNGB_CUDA_OK(cudaStreamWaitEvent(s, c.side_ev[4], 0));
     }
-
-    AdlerParams ap{ws.row_adler, ws.st, d_out, out_stride, w, h, chans};
-    launch_adler_finalize(ap, n, s);
-    prof_mark(ps, kProfAdler, s);
-
-    CrcParams cp{};
-    cp.out = d_out; cp.out_stride = out_stride; cp.st = ws.st;
-    cp.max_tiles = crc_ctas_for(max_encoded_size(w, h, chans)); cp.msg_start = kPngHeaderSize - 4; cp.init_xor = 0xFFFFFFFFu;
-    if (fused && g_inline_crc) {
-        launch_fused_crc(ws.fused_desc, n, w, h, books, book_stride, ws.st, d_out, out_stride, s);   // combine the in-kernel partials
-        cp.stored_only = 1u;                                                // the file-reading CRC kernel is only needed for stored-block images
-        count_launch(1);
-    }
-    launch_crc(cp, n, s);
-    prof_mark(ps, kProfCrc, s);
-    count_launch(4);
     FPNGB_CUDA_OK(cudaGetLastError());
     return c.ws_release(s);
 }
@@ -367,6 +408,8 @@ int fpngb_init(int device)
     if (rc) return rc;
     rc = fused_tables_init();
     if (rc) return rc;
+    rc = crc_stream_tables_init();
+    if (rc) return rc;
     c.pin_small.pinned = true;
     rc = c.pin_small.reserve(1 << 16);
     if (rc) return rc;
@@ -384,7 +427,10 @@ size_t fpngb_max_encoded_size(uint32_t w, uint32_t h, uint32_t chans) { return m
 FPNGB_API void fpngb_debug_rows_per_warp(uint32_t v) { set_rows_per_warp16(v); }
 
 // test hook: 1 = use the two-kernel (scan + pack) encoder even where the single-pass encoder applies; not part of the reference surface
-FPNGB_API void fpngb_debug_disable_fused(int off) { g_no_fused_override = off != 0; }
+FPNGB_API void fpngb_debug_disable_fused(int off) { g_fused_mode = off ? 0 : 1; }
+FPNGB_API void fpngb_debug_use_fused(int mode) { g_fused_mode = mode; }
+FPNGB_API void fpngb_debug_crc_overlap(int on) { g_crc_overlap = on != 0; }
+FPNGB_API void fpngb_debug_crc_stream(int on) { g_crc_stream = on != 0; }
 FPNGB_API void fpngb_debug_inline_crc(int on) { g_inline_crc = on != 0; }
 
 // exposes the static code books to the tests (sizes[288], codes[288]); not part of the reference surface
@@ -532,7 +578,7 @@ FPNGB_API int fpngb_profile_read(float* ms, int nslots)
 {
     std::lock_guard<std::mutex> lk(g_ctx.mu);
     double sum[kProfSlots] = {0};
-    int calls = 0;
+    uint64_t first_call = ~0ull, last_call = 0;
     for (ProfSet* ps : g_prof_sets) {
         int last = 0;   // index of the last recorded event
         cudaEventSynchronize(ps->ev[0]);
@@ -540,12 +586,16 @@ FPNGB_API int fpngb_profile_read(float* ms, int nslots)
             if (!ps->used[i]) continue;
             float t = 0;
             cudaEventSynchronize(ps->ev[i + 1]);
-            if (cudaEventElapsedTime(&t, ps->ev[last], ps->ev[i + 1]) == cudaSuccess) sum[i] += t;
-            last = i + 1;
+            // the CRC of a chunk may run on the side stream, overlapped with the next chunk: its own start event brackets it
+            cudaEvent_t from = (i == kProfCrc && ps->crc_side) ? ps->crc_start : ps->ev[last];
+            if (cudaEventElapsedTime(&t, from, ps->ev[i + 1]) == cudaSuccess) sum[i] += t;
+            if (!(i == kProfCrc && ps->crc_side)) last = i + 1;
         }
-        calls++;
+        if (ps->call < first_call) first_call = ps->call;
+        if (ps->call > last_call) last_call = ps->call;
         g_prof_free.push_back(ps);
     }
+    const int calls = g_prof_sets.empty() ? 0 : (int)(last_call - first_call + 1);
     g_prof_sets.clear();
     for (int i = 0; i < nslots && i < kProfSlots; i++) ms[i] = calls ? (float)(sum[i] / calls) : 0.f;
     return calls;

@@ -82,6 +82,9 @@ int launch_encode_fused(const uint8_t* pixels, size_t image_stride, uint32_t n, 
 void launch_fused_crc(const void* desc_mem, uint32_t n, uint32_t w, uint32_t h, const CodeBook* books, uint32_t book_stride, const ImageState* st,
                       uint8_t* out, size_t out_stride, cudaStream_t s);
 int fused_tables_init();
+// second-generation IDAT CRC kernel (crc_stream_kernel.cu)
+int crc_stream_tables_init();
+void launch_crc_stream(const CrcParams& p, uint32_t n, size_t max_file_bytes, cudaStream_t s);
 
 void launch_scan(const ScanParams& p, uint32_t n, uint32_t chans, int mode, bool hist, cudaStream_t s);
 bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t chans);

@@ -10,7 +10,12 @@ done
 echo "=== LIT64=1 (default build)"; run_all
 echo "=== LIT64=0"; FPNGB_NVCC_DEFS=-DFPNGB_LIT64=0 python -c "
 from fpng_b200 import _build; _build.build(force=True)" 2>&1 | tail -2
-run_all
+timeout 250 python tests/gpu_fused_check.py inline 2>&1 | tail -4
+for a in "c2 g1" "c3 g1"; do set -- $a
+timeout 200 python bench.py --workload $1 --kind $2 --no-cpu --no-decode --steps 20 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); print('$1 $2', d['value'], d['ms_per_step'], d.get('kernels_ms'), d['config'].get('parity_image0_vs_oracle'))"
+done
 echo "=== decode tests + bench decode leg (default build again)"
 python -c "
 from fpng_b200 import _build; _build.build(force=True)" 2>&1 | tail -2

@@ -9,7 +9,8 @@ from fpng_b200._lib import lib
 L = lib()
 mode = sys.argv[1] if len(sys.argv) > 1 else "inline"
 L.fpngb_debug_inline_crc(1 if mode == "inline" else 0)
-L.fpngb_debug_disable_fused(1 if mode == "old" else 0)
+L.fpngb_debug_use_fused(0 if mode in ("old", "old_serial") else 1)
+L.fpngb_debug_crc_overlap(0 if mode == "old_serial" else 1)
 print("mode", mode)
 bad = 0; n = 0
 shapes = [(16, 1), (16, 2), (32, 3), (512, 9), (528, 17), (1024, 5), (1040, 33), (1920, 8), (2048, 4), (4096, 3), (4080, 7), (3840, 5), (64, 300), (1536, 11),

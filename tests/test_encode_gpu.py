@@ -248,7 +248,7 @@ def test_random_dimension_fuzz_like_reference_E(gpu, oracle):
                 assert st == 0
 
 
-@pytest.mark.parametrize("mode", ["fused+inline_crc", "fused", "two_kernel"])
+@pytest.mark.parametrize("mode", ["fused+inline_crc", "fused", "two_kernel", "two_kernel_serial_crc"])
 def test_encoder_generations_agree_with_oracle(gpu, oracle, mode):
     """The single-pass encoder (encode_fused.cu: decoupled look-back, lane-local bit strings, in-kernel CRC partials), the same
     with the file-reading CRC kernel, and the two-kernel scan + pack encoder must all write the reference's bytes."""
@@ -256,7 +256,8 @@ def test_encoder_generations_agree_with_oracle(gpu, oracle, mode):
     from fpng_b200._lib import lib
     L = lib()
     L.fpngb_debug_inline_crc(1 if mode == "fused+inline_crc" else 0)
-    L.fpngb_debug_disable_fused(1 if mode == "two_kernel" else 0)
+    L.fpngb_debug_use_fused(1 if mode.startswith("fused") else 0)
+    L.fpngb_debug_crc_overlap(0 if mode == "two_kernel_serial_crc" else 1)
     try:
         # aligned and unaligned scanlines (the single-pass kernel has a staged-tile and a direct-load variant), partial units,
         # widths beyond its reach (> 4096: two-kernel encoder), one-pixel and one-row images
@@ -267,21 +268,33 @@ def test_encoder_generations_agree_with_oracle(gpu, oracle, mode):
             for (w, h) in shapes:
                 for c in (3, 4):
                     for flags in (0, 1):
-                        imgs = np.stack([imagegen.make(kind, w, h, c, 3 + i) for i in range(3)])
+                        nimg = 17 if (w, h) == (512, 9) else 3      # >= 16 images: the chunked path with the CRC on the side stream
+                        imgs = np.stack([imagegen.make(kind, w, h, c, 3 + i) for i in range(nimg)])
                         out, sizes = gpu.encode_batch_device(torch.from_numpy(imgs).cuda(), flags)
                         torch.cuda.synchronize()
                         sz = sizes.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
                         oh = out.cpu().numpy()
-                        for i in range(3):
+                        for i in range(nimg):
                             assert oh[i, : sz[i]].tobytes() == oracle.encode(imgs[i], w, h, c, flags), (mode, kind, w, h, c, flags, i)
     finally:
         L.fpngb_debug_inline_crc(1)
-        L.fpngb_debug_disable_fused(0)
+        L.fpngb_debug_use_fused(-1)
+        L.fpngb_debug_crc_overlap(1)
 
 
 def test_single_pass_encoder_many_groups(gpu, ref):
-    """Long look-back chains: tall images (thousands of row groups per image) and a batch mixing compressible images with
+    """(single-pass encoder selected explicitly) Long look-back chains: tall images (thousands of row groups per image) and a batch mixing compressible images with
     ones that fall back to stored blocks after the single-pass kernel already wrote into their buffers."""
+    import torch
+    from fpng_b200._lib import lib
+    lib().fpngb_debug_use_fused(1)
+    try:
+        _many_groups(gpu, ref)
+    finally:
+        lib().fpngb_debug_use_fused(-1)
+
+
+def _many_groups(gpu, ref):
     import torch
     for (w, h, c) in ((512, 6000, 3), (1024, 3000, 4), (4096, 700, 4)):
         kinds = ["g1", "g2", "g0", "runs", "g2", "mut"]
