@@ -24,6 +24,10 @@ template <int CHANS> __host__ __device__ constexpr int stage16_words() { return 
 __device__ __forceinline__ uint32_t byte1(uint32_t v) { return __byte_perm(v, 0u, 0x4441); }   // (v >> 8) & 0xFF in one PRMT
 __device__ __forceinline__ uint32_t byte2(uint32_t v) { return __byte_perm(v, 0u, 0x4442); }
 
+// scanline loader: staged tiles (TMA / cp.async) for 16-byte aligned scanlines, direct realigning 128-bit loads for any other shape
+template <int CHANS, bool DIRECT> struct Loader16 { using type = Walk16<CHANS>; };
+template <int CHANS> struct Loader16<CHANS, true> { using type = Walk16Direct<CHANS>; };
+
 template <int CHANS>
 __device__ __forceinline__ uint32_t literal_bits16(const uint8_t* s_lit, uint32_t px)
 {
@@ -36,12 +40,13 @@ __device__ __forceinline__ uint32_t literal_bits16(const uint8_t* s_lit, uint32_
 // ------------------------------------------------------------------------------------------------
 // K1 (v2): per-row bit count + Adler partials (+ per-lane bit offsets inside the row for the pack kernel)
 // ------------------------------------------------------------------------------------------------
-template <int CHANS>
+template <int CHANS, bool DIRECT>
 __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams p)
 {
+    using WK = typename Loader16<CHANS, DIRECT>::type;
     constexpr uint32_t M = max_match_pixels(CHANS);
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    uint8_t* s_lit = dyn_smem + kScan16Rows * Walk16<CHANS>::kWarpBytes;
+    uint8_t* s_lit = dyn_smem + kScan16Rows * WK::kWarpBytes;
     uint8_t* s_match = s_lit + 256;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -58,10 +63,10 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
     const uint8_t* prev = y ? cur - bpl : nullptr;
     const uint32_t filt = y ? 2u : 0u;
     const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
-    uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
+    uint8_t* tiles = dyn_smem + warp * WK::kWarpBytes;
     uint2* lane_ofs = p.lane_ofs + ((size_t)img * p.h + y) * p.lane_ofs_pitch;
 
-    Walk16<CHANS> wk; wk.init(lane, tiles);
+    WK wk; wk.init(lane, tiles); wk.bind(cur, prev);
     RowCarry carry = {0u, 0u};
     uint32_t row_run = s_lit[filt];              // bits of the row emitted before the current step (filter literal first)
     uint32_t sumA = 0, last_unit = 0;
@@ -69,10 +74,10 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
 
     wk.prefetch(cur, prev, 0, bpl, lane, tiles);
     for (uint32_t step = 0; step < nsteps; step++) {
-        uint32_t dw[Walk16<CHANS>::kWords], px[16];
+        uint32_t dw[WK::kWords], px[16];
         wk.template consume<true>(prev != nullptr, step, step, bpl, lane, tiles, dw, sumA, sumB);
         if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);         // lands while this step is processed
-        Walk16<CHANS>::pixels(dw, px);
+        WK::pixels(dw, px);
         const uint32_t p0 = step * kStep16 + lane * kPix16;
         const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
 
@@ -143,12 +148,13 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
 // K1-hist (v2): 288-bin literal/length histogram of 2-pass mode (fpng.cpp:1021-1084, 1299-1363) on the 16-pixel walker.
 // Warp-private shared-memory histograms (no inter-warp contention), merged per CTA, then added to the image's bins.
 // ------------------------------------------------------------------------------------------------
-template <int CHANS>
+template <int CHANS, bool DIRECT>
 __global__ void __launch_bounds__(32 * kScan16Rows) row_hist16_kernel(ScanParams p)
 {
+    using WK = typename Loader16<CHANS, DIRECT>::type;
     constexpr uint32_t M = max_match_pixels(CHANS);
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    uint32_t* s_hist_all = reinterpret_cast<uint32_t*>(dyn_smem + kScan16Rows * Walk16<CHANS>::kWarpBytes);   // [warps][288]
+    uint32_t* s_hist_all = reinterpret_cast<uint32_t*>(dyn_smem + kScan16Rows * WK::kWarpBytes);   // [warps][288]
     __shared__ uint16_t s_lensym[88];
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -164,17 +170,17 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_hist16_kernel(ScanParams
         const uint8_t* cur = p.pixels + (size_t)img * p.image_stride + (size_t)y * bpl;
         const uint8_t* prev = y ? cur - bpl : nullptr;
         const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
-        uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
-        Walk16<CHANS> wk; wk.init(lane, tiles);
+        uint8_t* tiles = dyn_smem + warp * WK::kWarpBytes;
+        WK wk; wk.init(lane, tiles); wk.bind(cur, prev);
         RowCarry carry = {0u, 0u};
         uint32_t dummyA = 0; unsigned long long dummyB = 0;
         if (lane == 0) atomicAdd(&hist[y ? 2 : 0], 1u);               // the filter literal
         wk.prefetch(cur, prev, 0, bpl, lane, tiles);
         for (uint32_t step = 0; step < nsteps; step++) {
-            uint32_t dw[Walk16<CHANS>::kWords], px[16];
+            uint32_t dw[WK::kWords], px[16];
             wk.template consume<false>(prev != nullptr, step, step, bpl, lane, tiles, dw, dummyA, dummyB);
             if (step + 1 < nsteps) wk.prefetch(cur, prev, step + 1, bpl, lane, tiles);
-            Walk16<CHANS>::pixels(dw, px);
+            WK::pixels(dw, px);
             const uint32_t p0 = step * kStep16 + lane * kPix16;
             const Lane16 t = classify16<CHANS>(px, p0, w, carry, lane);
             if (__any_sync(kFullMask, t.litm != 0)) {
@@ -335,18 +341,19 @@ __device__ __forceinline__ void put_event16(BitStager16& bs, uint32_t s_match_sa
     if (len) put_match16(bs, s_match_saddr, len);
 }
 
-template <int CHANS>
+template <int CHANS, bool DIRECT>
 __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParams p, uint32_t rows_per_warp)
 {
+    using WK = typename Loader16<CHANS, DIRECT>::type;
     if (p.stored_only && !p.st[blockIdx.y].stored) return;     // after the fused encoder only stored-block images are left to write
     constexpr uint32_t M = max_match_pixels(CHANS);
     constexpr int kHalfWords = 2 * CHANS;        // filtered words of 8 pixels
     extern __shared__ __align__(16) uint8_t dyn_smem[];
 #if FPNGB_PACK_LIT64
-    uint32_t* s_lit64 = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * Walk16<CHANS>::kWarpBytes);   // [512][2]: (code, size) + null half
+    uint32_t* s_lit64 = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * WK::kWarpBytes);   // [512][2]: (code, size) + null half
     uint32_t* s_lit = s_lit64 + 1024;                // [512]: 256 packed entries + 256 zeros
 #else
-    uint32_t* s_lit = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * Walk16<CHANS>::kWarpBytes);   // [512]: 256 entries + 256 zeros
+    uint32_t* s_lit = reinterpret_cast<uint32_t*>(dyn_smem + kPack16Rows * WK::kWarpBytes);   // [512]: 256 entries + 256 zeros
 #endif
     uint32_t* s_match = s_lit + 512;
     uint32_t* s_stage_all = s_match + 88;
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     const uint8_t* img_px = p.pixels + (size_t)img * p.image_stride;
     uint32_t* stage = s_stage_all + warp * stage16_words<CHANS>();
     const uint32_t stage_s = smem_u32(stage), lit_s = smem_u32(s_lit), match_s = smem_u32(s_match);
-    uint8_t* tiles = dyn_smem + warp * Walk16<CHANS>::kWarpBytes;
+    uint8_t* tiles = dyn_smem + warp * WK::kWarpBytes;
     const uint32_t nsteps = (w + kStep16 - 1) / kStep16;
     const uint32_t nitems = nrows * nsteps;      // (scanline, step) work items of this warp, walked as one pipelined sequence
     // per-row constants of all this warp's rows, one row per lane (broadcast at the row's first step)
@@ -394,7 +401,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     uint32_t flushed_bits = 0;                   // row bits (incl. the G & 31 lead-in) already flushed to global, multiple of 32
     uint32_t leftover = 0;                       // bits of the partially filled word carried from the previous step (lane 0 seeds with it)
 
-    Walk16<CHANS> wk; wk.init(lane, tiles);
+    WK wk; wk.init(lane, tiles);
     uint32_t dummyA = 0; unsigned long long dummyB = 0;
     {
         const uint8_t* c0 = img_px + (size_t)row0 * bpl;
@@ -411,7 +418,8 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
             g31 = (uint32_t)(G & 31ull);
             first_pending = true; flushed_bits = 0; leftover = 0;
         }
-        uint32_t dw[Walk16<CHANS>::kWords];
+        uint32_t dw[WK::kWords];
+        { const uint8_t* cc = img_px + (size_t)y * bpl; wk.bind(cc, y ? cc - bpl : nullptr); }
         wk.template consume<false>(y != 0, item, step, bpl, lane, tiles, dw, dummyA, dummyB);
         // the next item (possibly the first step of the next scanline) is fetched while this one is emitted
         const bool more = step + 1 < nsteps;     // more steps in this row
@@ -551,32 +559,42 @@ bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t
     return ((uintptr_t)base % 16 == 0) && (image_stride % 16 == 0) && (bpl % 16 == 0);
 }
 
-template <int CHANS> constexpr size_t scan16_smem() { return kScan16Rows * Walk16<CHANS>::kWarpBytes + 256 + 96; }
-template <int CHANS> constexpr size_t pack16_smem() { return kPack16Rows * Walk16<CHANS>::kWarpBytes + ((FPNGB_PACK_LIT64 ? 1024 : 0) + 512 + 88 + kPack16Rows * stage16_words<CHANS>()) * 4; }
+template <int CHANS, bool DIRECT> constexpr size_t scan16_smem() { return kScan16Rows * Loader16<CHANS, DIRECT>::type::kWarpBytes + 256 + 96; }
+template <int CHANS, bool DIRECT> constexpr size_t pack16_smem()
+{
+    return kPack16Rows * Loader16<CHANS, DIRECT>::type::kWarpBytes + ((FPNGB_PACK_LIT64 ? 1024 : 0) + 512 + 88 + kPack16Rows * stage16_words<CHANS>()) * 4;
+}
+template <int CHANS, bool DIRECT> constexpr size_t hist16_smem() { return kScan16Rows * Loader16<CHANS, DIRECT>::type::kWarpBytes + kScan16Rows * 288 * 4; }
 
+// The 16-pixel kernels take any scanline alignment: `direct` selects the realigning-load variant (walk16_eligible() false).
+#define FPNGB_LAUNCH16(kernel, smemfn, grid, threads, ...) do { \
+        if (chans == 4) { if (direct) { FPNGB_SET_SMEM((kernel<4, true>), (smemfn<4, true>())); kernel<4, true><<<grid, threads, smemfn<4, true>(), s>>>(__VA_ARGS__); } \
+                          else { FPNGB_SET_SMEM((kernel<4, false>), (smemfn<4, false>())); kernel<4, false><<<grid, threads, smemfn<4, false>(), s>>>(__VA_ARGS__); } } \
+        else { if (direct) { FPNGB_SET_SMEM((kernel<3, true>), (smemfn<3, true>())); kernel<3, true><<<grid, threads, smemfn<3, true>(), s>>>(__VA_ARGS__); } \
+               else { FPNGB_SET_SMEM((kernel<3, false>), (smemfn<3, false>())); kernel<3, false><<<grid, threads, smemfn<3, false>(), s>>>(__VA_ARGS__); } } \
+    } while (0)
 
 void launch_scan16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
     // one scanline per warp: the multi-scanline sequence that pays off in the pack kernel measured neutral (RGB) to 4 % slower (RGBA) here
+    const bool direct = !walk16_eligible(p.pixels, p.image_stride, p.w, chans);
     dim3 grid((p.h + kScan16Rows - 1) / kScan16Rows, n);
-    if (chans == 4) { FPNGB_SET_SMEM(row_scan16_kernel<4>, scan16_smem<4>()); row_scan16_kernel<4><<<grid, 32 * kScan16Rows, scan16_smem<4>(), s>>>(p); }
-    else { FPNGB_SET_SMEM(row_scan16_kernel<3>, scan16_smem<3>()); row_scan16_kernel<3><<<grid, 32 * kScan16Rows, scan16_smem<3>(), s>>>(p); }
+    FPNGB_LAUNCH16(row_scan16_kernel, scan16_smem, grid, 32 * kScan16Rows, p);
 }
 
-template <int CHANS> constexpr size_t hist16_smem() { return kScan16Rows * Walk16<CHANS>::kWarpBytes + kScan16Rows * 288 * 4; }
 void launch_hist16(const ScanParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
+    const bool direct = !walk16_eligible(p.pixels, p.image_stride, p.w, chans);
     dim3 grid((p.h + kScan16Rows - 1) / kScan16Rows, n);
-    if (chans == 4) { FPNGB_SET_SMEM(row_hist16_kernel<4>, hist16_smem<4>()); row_hist16_kernel<4><<<grid, 32 * kScan16Rows, hist16_smem<4>(), s>>>(p); }
-    else { FPNGB_SET_SMEM(row_hist16_kernel<3>, hist16_smem<3>()); row_hist16_kernel<3><<<grid, 32 * kScan16Rows, hist16_smem<3>(), s>>>(p); }
+    FPNGB_LAUNCH16(row_hist16_kernel, hist16_smem, grid, 32 * kScan16Rows, p);
 }
 
 void launch_pack16(const PackParams& p, uint32_t n, uint32_t chans, cudaStream_t s)
 {
+    const bool direct = !walk16_eligible(p.pixels, p.image_stride, p.w, chans);
     const uint32_t rpw = rows_per_warp16(n, p.h), rows_per_cta = kPack16Rows * rpw;
     dim3 grid((p.h + rows_per_cta - 1) / rows_per_cta, n);
-    if (chans == 4) { FPNGB_SET_SMEM(pack_rows16_kernel<4>, pack16_smem<4>()); pack_rows16_kernel<4><<<grid, 32 * kPack16Rows, pack16_smem<4>(), s>>>(p, rpw); }
-    else { FPNGB_SET_SMEM(pack_rows16_kernel<3>, pack16_smem<3>()); pack_rows16_kernel<3><<<grid, 32 * kPack16Rows, pack16_smem<3>(), s>>>(p, rpw); }
+    FPNGB_LAUNCH16(pack_rows16_kernel, pack16_smem, grid, 32 * kPack16Rows, p, rpw);
 }
 
 }  // namespace fpngb

@@ -270,7 +270,9 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
     // RGBA 1-pass under a table where a one-pixel match can lose against four literals: only the generic kernels
     // implement the reference's check (fpng.cpp:1520-1528); it cannot fire with the shipped table
     const uint32_t lit1_rule = (!two_pass && chans == 4 && c.h_static_books[1].lit1_rule) ? 1u : 0u;
-    const bool v2 = !force_generic && !lit1_rule && walk16_eligible(d_pixels, image_stride, w, chans);
+    // the 16-pixel kernels take any scanline alignment (staged-tile loader for 16-byte aligned scanlines, direct realigning
+    // loads otherwise); the generic 4-pixel kernels remain for the trained-table rule and for A/B tests
+    const bool v2 = !force_generic && !lit1_rule;
     const bool want_fused = g_fused_mode == 1 || (g_fused_mode < 0 && env_fused);
     const bool fused = want_fused && !force_generic && !lit1_rule && !(flags & FPNGB_FORCE_UNCOMPRESSED) &&
                        fused_eligible(d_pixels, image_stride, w, h, chans, n);
@@ -718,7 +720,8 @@ int fpngb_train_accumulate_device(const void* d_pixels, size_t image_stride, uin
     sp.pixels = (const uint8_t*)d_pixels; sp.image_stride = image_stride; sp.w = w; sp.h = h; sp.books = c.d_static_books; sp.book_stride = 0;
     sp.row_bits = ws.row_bits; sp.row_adler = ws.row_adler; sp.st = ws.st; sp.hist = ws.hist; sp.lane_ofs = ws.lane_ofs; sp.lane_ofs_pitch = ws.lane_ofs_pitch;
     FPNGB_CUDA_OK(cudaMemsetAsync(ws.hist, 0, (size_t)n * 288 * 4, s));
-    if (walk16_eligible(d_pixels, image_stride, w, chans)) launch_hist16(sp, n, chans, s);
+    static const bool force_generic_t = getenv("FPNGB_FORCE_GENERIC") && atoi(getenv("FPNGB_FORCE_GENERIC")) != 0;
+    if (!force_generic_t) launch_hist16(sp, n, chans, s);
     else launch_scan(sp, n, chans, pick_load_mode(d_pixels, image_stride, w, chans), true, s);
     count_launch(1);
     std::vector<uint32_t> hh((size_t)n * 288);

@@ -75,8 +75,10 @@ def test_cli_csv_and_decode_only(exe, tmp_path):
     assert f[0] == EXAMPLE and f[1:4] == ["687", "1012", "3"] and len(f) == 9 and float(f[7]) > 0 and float(f[8]) > 0
     assert run(exe, "-f", EXAMPLE).returncode == 0
     bad = tmp_path / "bad.png"
-    d = bytearray(open(EXAMPLE, "rb").read()); d[4000] ^= 0x55
+    d = bytearray(open(EXAMPLE, "rb").read()); d[18] ^= 0x55          # IHDR width: header CRC-32 mismatch (the IDAT CRC is not checked by fpng decoders)
     bad.write_bytes(bytes(d))
+    assert run(exe, "-f", str(bad)).returncode != 0
+    bad.write_bytes(open(EXAMPLE, "rb").read()[:-40])                    # truncated stream
     assert run(exe, "-f", str(bad)).returncode != 0
 
 
