@@ -234,7 +234,13 @@ __device__ __forceinline__ void stage_window(Stream& st, uint32_t* s_win, unsign
 {
     const unsigned long long w0 = first_sub * (kSubBits / 32);
     const uint32_t base = (uint32_t)(w0 >= kWinLead ? w0 - kWinLead : 0ull);
-    for (uint32_t i = threadIdx.x; i < kWinWords; i += blockDim.x) s_win[i + (i >> 5)] = __ldg(st.words + min(base + i, st.max_widx));
+    // word i lives at s_win[i + i / 32]; the pad slot in front of every 32-word block holds a COPY of the block's first word, so
+    // that (address, address + 1) always are two consecutive stream words (win_peek below reads 32 bits at any bit position)
+    for (uint32_t i = threadIdx.x; i < kWinWords; i += blockDim.x) {
+        const uint32_t v = __ldg(st.words + min(base + i, st.max_widx));
+        s_win[i + (i >> 5)] = v;
+        if ((i & 31u) == 0u && i) s_win[i + (i >> 5) - 1u] = v;
+    }
     st.swin = s_win; st.sw_base = base; st.sw_count = kWinWords;
 }
 
@@ -420,12 +426,63 @@ __device__ __forceinline__ SubScan decode_range(const Stream& st, const uint32_t
 // Output state is three 32-bit values (row, data column, pending-byte accumulator) and a row pointer; bytes are gathered into
 // aligned 32-bit stores (a thread's unaligned head bytes and a row's tail bytes go out singly, so neighbouring threads
 // never touch the same word).  Same acceptance rules as decode_range<true> (fpng.cpp:2264, 2302-2315, 2642, 2681-2691, 2727).
+// ---- lean token loops on the shared-memory window -------------------------------------------------------------------
+// With the stream staged in shared memory a decoder needs no bit buffer: 32 fresh bits at ANY bit position are two shared
+// loads and one funnel shift, and the only state carried from token to token is the bit position itself.
+__device__ __forceinline__ uint32_t win_peek(const uint32_t* __restrict__ win, uint32_t q)     // q: bit offset from the window's first word
+{
+    const uint32_t si = q >> 5, a = si + (si >> 5);
+    return __funnelshift_r(win[a], win[a + 1u], q);                         // shift amount taken modulo 32
+}
+
+// Scan pass on the window: same contract as decode_range<false>.  `O` = bit offset of abs_origin inside the window.
+__device__ __forceinline__ SubScan scan_window(const uint32_t* __restrict__ win, uint32_t O, const uint32_t* __restrict__ s_lut,
+                                               uint32_t rel, uint32_t lo, uint32_t hi)
+{
+    SubScan r; r.first = lo; r.exit = 0; r.eob_end = 0; r.n_out = 0; r.nlit = 0; r.lits = 0;
+    while (rel < lo) {                                                       // pre-roll: lock on to the token grid
+        const uint32_t e = s_lut[win_peek(win, O + rel) & 4095u];
+        uint32_t l = lut_len0(e);
+        const uint32_t s = lut_sym0(e);
+        if (!l || s == 256u || s > 285u) { rel = lo; break; }
+        if (s > 256u) l += c_len_xbits[s - 257u] + 1u;
+        rel += l;
+    }
+    r.first = rel;
+    uint32_t lits = 0, n_out = 0, nlit = 0;
+    while (rel < hi) {
+        const uint32_t w = win_peek(win, O + rel);
+        const uint32_t e = s_lut[w & 4095u];
+        const uint32_t l0 = lut_len0(e), s = lut_sym0(e);
+        if (!l0) { r.exit = kRelErr; r.n_out = n_out; r.nlit = nlit; r.lits = lits; return r; }
+        if (s < 256u) {
+            const uint32_t l1 = lut_len1(e);
+            lits = (lits >> 8) | (s << 24);
+            if (l1 && (rel + l0 < hi)) { rel += l0 + l1; n_out += 2u; nlit += 2u; lits = (lits >> 8) | (lut_sym1(e) << 24); }
+            else { rel += l0; n_out += 1u; nlit += 1u; }
+        } else if (s == 256u) {
+            rel += l0;
+            r.exit = kRelEnd; r.eob_end = rel; r.n_out = n_out; r.nlit = nlit; r.lits = lits;
+            return r;
+        } else {
+            if (s > 285u) { r.exit = kRelErr; r.n_out = n_out; r.nlit = nlit; r.lits = lits; return r; }
+            const uint32_t xb = c_len_xbits[s - 257u];
+            n_out += c_len_base[s - 257u] + ((w >> l0) & ((1u << xb) - 1u));
+            rel += l0 + xb + 1u;                                             // extra bits + the 1-bit distance code (fpng.cpp:2300)
+        }
+    }
+    r.exit = rel; r.n_out = n_out; r.nlit = nlit; r.lits = lits;
+    return r;
+}
+
 template <int CHANS>
 __device__ __forceinline__ void decode_write_range(const Stream& st, const uint32_t* __restrict__ s_lut, unsigned long long abs_origin, uint32_t hi,
                                                    uint8_t* __restrict__ delta, uint32_t pitch, uint32_t bpl, uint32_t h,
                                                    unsigned long long out_pos, uint32_t tail, uint32_t* err)
 {
-    Cursor c; c.seek(st, abs_origin);
+    // the subsequence lies inside the CTA's shared-memory window (stage_window): read it by bit position
+    const uint32_t* __restrict__ win = st.swin;
+    const uint32_t O = (uint32_t)(abs_origin - 32ull * st.sw_base);
     uint32_t rel = 0, lits = tail;
     uint32_t row = (uint32_t)(out_pos / (bpl + 1ull));
     const uint32_t col0 = (uint32_t)(out_pos % (bpl + 1ull));
@@ -451,25 +508,22 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
     } while (0)
 
     while (rel < hi) {
-        c.refill(st);
-        const uint32_t e = s_lut[(uint32_t)c.buf & 4095u];
+        const uint32_t w = win_peek(win, O + rel);
+        const uint32_t e = s_lut[w & 4095u];
         const uint32_t l0 = lut_len0(e), s = lut_sym0(e);
         if (!l0) return;                                                   // invalid code: the link pass already flagged it
         if (s < 256u) {
             const uint32_t l1 = lut_len1(e);
             const bool two = l1 && (rel + l0 < hi);
-            const uint32_t l = two ? l0 + l1 : l0;
-            c.skip(l); rel += l;
+            rel += two ? l0 + l1 : l0;
             FPNGB_LITERAL(s);
             if (two) FPNGB_LITERAL(lut_sym1(e));
         } else if (s == 256u) {
             break;
         } else {
             if (s > 285u) return;
-            c.skip(l0);
             const uint32_t xb = c_len_xbits[s - 257u];
-            const uint32_t run = c_len_base[s - 257u] + ((uint32_t)c.buf & ((1u << xb) - 1u));
-            c.skip(xb + 1u);
+            const uint32_t run = c_len_base[s - 257u] + ((w >> l0) & ((1u << xb) - 1u));
             rel += l0 + xb + 1u;
             const bool bad = row >= h || need_filter || dcol < (uint32_t)CHANS || (dcol % CHANS) != 0u || (run % CHANS) != 0u || dcol + run > bpl;
             if (bad) { *err = 1; return; }
@@ -536,10 +590,10 @@ __global__ void __launch_bounds__(kDecThreads) decode_scan_kernel(DecodeParams p
     unsigned long long origin;
     if (g == sp.g0) {            // the file's first subsequence starts exactly at the first token
         origin = sp.tok0;
-        r = decode_range<false>(sm, s_lut, origin, 0u, 0u, (uint32_t)((g + 1) * kSubBits - origin), p.chans, nullptr, 0, 0, 0, 0, 0, nullptr);
+        r = scan_window(s_win, (uint32_t)(origin - 32ull * sm.sw_base), s_lut, 0u, 0u, (uint32_t)((g + 1) * kSubBits - origin));
     } else {
         origin = lo_abs - kPreRoll < sp.tok0 ? sp.tok0 : lo_abs - kPreRoll;     // never pre-roll across the block header
-        r = decode_range<false>(sm, s_lut, origin, 0u, (uint32_t)(lo_abs - origin), (uint32_t)(lo_abs - origin) + kSubBits, p.chans, nullptr, 0, 0, 0, 0, 0, nullptr);
+        r = scan_window(s_win, (uint32_t)(origin - 32ull * sm.sw_base), s_lut, 0u, (uint32_t)(lo_abs - origin), (uint32_t)(lo_abs - origin) + kSubBits);
     }
     info->start = origin + r.first;
     info->exit = r.exit >= kRelErr ? (r.exit == kRelEnd ? kPosEnd : kPosErr) : origin + r.exit;
