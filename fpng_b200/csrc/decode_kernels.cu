@@ -489,15 +489,17 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
     bool need_filter = col0 == 0u;                     // the next byte of the filtered stream is the row's filter byte
     uint32_t dcol = col0 ? col0 - 1u : 0u;             // data bytes of the current row already produced
     uint8_t* rowp = delta + (size_t)row * pitch;
-    uint32_t acc = 0, nacc = 0;                        // pending bytes: data columns [dcol - nacc, dcol), first one 4-byte aligned
+    unsigned long long acc = 0; uint32_t nacc = 0;     // pending bytes: data columns [dcol - nacc, dcol), first one 4-byte aligned
 
+    // general byte sink: unaligned head bytes of the thread's range and a scanline's last bytes go out singly, everything else
+    // as aligned 32-bit words
 #define FPNGB_EMIT(v) do { \
         const uint32_t v__ = (v); \
-        if (nacc == 0u && (dcol & 3u)) rowp[dcol] = (uint8_t)v__;                                   /* unaligned head of this thread's range */ \
-        else { acc |= v__ << (8u * nacc); if (++nacc == 4u) { *reinterpret_cast<uint32_t*>(rowp + dcol - 3u) = acc; acc = 0u; nacc = 0u; } } \
-        if (++dcol == bpl) {                                                                          /* scanline complete */ \
+        if (nacc == 0u && (dcol & 3u)) rowp[dcol] = (uint8_t)v__; \
+        else { acc |= (unsigned long long)v__ << (8u * nacc); if (++nacc == 4u) { *reinterpret_cast<uint32_t*>(rowp + dcol - 3u) = (uint32_t)acc; acc = 0ull; nacc = 0u; } } \
+        if (++dcol == bpl) { \
             for (uint32_t i__ = 0; i__ < nacc; i__++) rowp[dcol - nacc + i__] = (uint8_t)(acc >> (8u * i__)); \
-            acc = 0u; nacc = 0u; row++; rowp += pitch; dcol = 0u; need_filter = true; \
+            acc = 0ull; nacc = 0u; row++; rowp += pitch; dcol = 0u; need_filter = true; \
         } \
     } while (0)
 #define FPNGB_LITERAL(v) do { \
@@ -515,7 +517,20 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
         if (s < 256u) {
             const uint32_t l1 = lut_len1(e);
             const bool two = l1 && (rel + l0 < hi);
+            const uint32_t cnt = two ? 2u : 1u;
             rel += two ? l0 + l1 : l0;
+            // fast path (almost every literal): inside a scanline, the pending bytes word aligned -- append one or two bytes to the
+            // 64-bit accumulator, store a word when four are there; no per-byte branches
+            if (!need_filter && (nacc | ((dcol & 3u) == 0u)) && dcol + cnt < bpl && row < h) {
+                const uint32_t s1 = lut_sym1(e);
+                lits = (lits >> 8) | (s << 24);
+                uint32_t v = s;
+                if (two) { lits = (lits >> 8) | (s1 << 24); v |= s1 << 8; }
+                acc |= (unsigned long long)v << (8u * nacc);
+                nacc += cnt; dcol += cnt;
+                if (nacc >= 4u) { *reinterpret_cast<uint32_t*>(rowp + dcol - nacc) = (uint32_t)acc; acc >>= 32; nacc -= 4u; }
+                continue;
+            }
             FPNGB_LITERAL(s);
             if (two) FPNGB_LITERAL(lut_sym1(e));
         } else if (s == 256u) {
@@ -536,7 +551,25 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
                 dcol += run;
                 if (dcol == bpl) { row++; rowp += pitch; dcol = 0u; need_filter = true; }
             } else {
-                for (uint32_t i = 0; i < run; i += 3) { FPNGB_EMIT(px & 0xFFu); FPNGB_EMIT((px >> 8) & 0xFFu); FPNGB_EMIT(px >> 16); }
+                // RGB: the 3-byte pixel repeats with a period of three 32-bit words.  Bytes up to the next word boundary go through
+                // the byte sink, whole words are stored from three rotating pattern registers, the remainder again byte-wise.
+                uint32_t left = run, ph = 0;                                  // ph: index inside the pixel of the next byte
+                while (left && ((dcol & 3u) || nacc)) { FPNGB_EMIT((px >> (8u * ph)) & 0xFFu); ph = ph == 2u ? 0u : ph + 1u; left--; }
+                if (left >= 4u) {
+                    uint32_t wa = 0, wb = 0, wc = 0;
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; j++) {
+                        wa |= ((px >> (8u * ((ph + j) % 3u))) & 0xFFu) << (8u * j);
+                        wb |= ((px >> (8u * ((ph + 4u + j) % 3u))) & 0xFFu) << (8u * j);
+                        wc |= ((px >> (8u * ((ph + 8u + j) % 3u))) & 0xFFu) << (8u * j);
+                    }
+                    const uint32_t nwords = left >> 2;
+                    uint32_t* d = reinterpret_cast<uint32_t*>(rowp + dcol);
+                    for (uint32_t k = 0; k < nwords; k++) { d[k] = wa; const uint32_t t = wa; wa = wb; wb = wc; wc = t; }
+                    dcol += nwords << 2; left -= nwords << 2; ph = (ph + nwords) % 3u;      // 4 bytes advance the phase by 1
+                    if (dcol == bpl) { row++; rowp += pitch; dcol = 0u; need_filter = true; }   // a run may end exactly at the end of its scanline
+                }
+                while (left) { FPNGB_EMIT((px >> (8u * ph)) & 0xFFu); ph = ph == 2u ? 0u : ph + 1u; left--; }
             }
         }
     }
