@@ -344,7 +344,11 @@ def run_ours(args, wl):
     L.fpngb_profile_read(prof, 9)
     L.fpngb_profile_enable(0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank_ms = None
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     total_pixels = world * n * w * h * args.steps
@@ -386,7 +390,9 @@ def run_ours(args, wl):
                    "l2": "inputs larger than L2 (%.0f MB per step)" % (in_bytes / 1e6) if in_bytes > 126e6 else "input smaller than L2: L2-warm",
                    "out_over_in": out_bytes / in_bytes, "parity_image0_vs_oracle": parity,
                    "g1_noise": "gradient + uniform integer noise in [-3, 3] from numpy RandomState(1234 + i % 16).randint (MT19937; SURVEY 8d words it as std::mt19937(1234 + i): same engine, different integer mapping, 16 distinct noise fields per batch); both arms use this generator"},
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches), "per_rank_ms_per_step": per_rank_ms,
+        "scaling_note": None if world == 1 else "weak scaling, no data-path collective: every rank encodes its own 128-image shard; --gpus 1 defaults to C2 "
+                        "(BASELINE config 2), --gpus N>1 to C3 (config 3): compare with `--gpus 1 --workload c3` (profiles/README.md) for the same-workload N=1 value",
         "kernels_ms": kern, "roofline": roof(dominant), "roofline_scan": roof("fused" if fused_path else "scan"),
         "encoder": "single-pass fused kernel (encode_fused.cu: filter + match + code emission + bit placement in one read of the pixels)" if fused_path
                    else "two-kernel scan + pack",
