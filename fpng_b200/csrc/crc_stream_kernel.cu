@@ -17,8 +17,8 @@
 
 namespace fpngb {
 
-constexpr uint32_t kCs2WarpWords = 8192;          // 32 KiB per warp (amortises the 32 KiB table fill of the CTA)
-constexpr uint32_t kCs2Warps = 8;                 // 256 KiB per CTA
+constexpr uint32_t kCs2WarpWords = 2048;          // 8 KiB per warp
+constexpr uint32_t kCs2Warps = 8;                 // 64 KiB per CTA
 constexpr uint32_t kCs2CtaWords = kCs2WarpWords * kCs2Warps;
 constexpr uint32_t kCs2FirstWord = (kPngHeaderSize - 4u) / 4u;      // word 13 holds file bytes 52..55: bytes 52, 53 (IDAT length) are masked off
 
@@ -63,10 +63,9 @@ __device__ __forceinline__ uint32_t mul_nib(const uint32_t (*t)[16], uint32_t a)
 // grid (max CTAs per image, n images); only images with st.stored == want_stored (or all when want_stored < 0) are processed
 __global__ void __launch_bounds__(32 * kCs2Warps) idat_crc_stream_kernel(CrcParams p)
 {
-    // 8 copies of the four slice tables, interleaved so that the 4 lanes sharing copy r = lane / 4 only touch banks
-    // {r, r + 8, r + 16, r + 24}: lane groups never conflict with each other (32 KiB; a single copy is ~3.5-way conflicted
-    // under random bytes and made shared-memory wavefronts the limiter: 0.38 ms -> measured below)
-    extern __shared__ __align__(16) uint32_t s_f8[];                        // [4][256][8]
+    // one copy of the four slice tables (4 KiB).  Eight bank-disjoint copies (32 KiB, lanes l / 4 sharing a copy) were measured:
+    // C2 0.380 -> 0.372 ms, but small files (one CTA per file) paid the 8x table fill (C2 G0 0.043 -> 0.064 ms): not kept.
+    __shared__ uint32_t s_f[4][256];
     __shared__ uint32_t s_part[kCs2Warps];
     const uint32_t img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     ImageState* st = p.st + img;
@@ -76,13 +75,8 @@ __global__ void __launch_bounds__(32 * kCs2Warps) idat_crc_stream_kernel(CrcPara
     const uint32_t nwords = wend - kCs2FirstWord;
     const uint32_t nctas = (nwords + kCs2CtaWords - 1) / kCs2CtaWords;
     if (blockIdx.x >= nctas) return;
-    for (uint32_t i = tid; i < 1024; i += blockDim.x) {
-        const uint32_t v = (&g2_f128b[0][0])[i];
-#pragma unroll
-        for (int r = 0; r < 8; r++) s_f8[i * 8u + r] = v;
-    }
+    for (uint32_t i = tid; i < 1024; i += blockDim.x) (&s_f[0][0])[i] = (&g2_f128b[0][0])[i];
     __syncthreads();
-    const uint32_t* tf = s_f8 + (lane >> 2);                                 // this lane's copy: entry (t, e) at tf[(t * 256 + e) * 8]
 
     const uint32_t* fw = reinterpret_cast<const uint32_t*>(p.out + (size_t)img * p.out_stride);
     // CTA b (counted from the END) covers words [wend - (b+1) * kCs2CtaWords, wend - b * kCs2CtaWords); warp m of it (from the end) 8 KiB
@@ -109,7 +103,7 @@ __global__ void __launch_bounds__(32 * kCs2Warps) idat_crc_stream_kernel(CrcPara
 #pragma unroll
             for (int q = 0; q < kBatch; q++) {
                 const uint32_t x = c ^ w[q];
-                if (k0 + q + 1 < kSteps) c = tf[(x & 0xFFu) << 3] ^ tf[(256u + ((x >> 8) & 0xFFu)) << 3] ^ tf[(512u + ((x >> 16) & 0xFFu)) << 3] ^ tf[(768u + (x >> 24)) << 3];
+                if (k0 + q + 1 < kSteps) c = s_f[0][x & 0xFFu] ^ s_f[1][(x >> 8) & 0xFFu] ^ s_f[2][(x >> 16) & 0xFFu] ^ s_f[3][x >> 24];
                 else c = x;
             }
         }
@@ -147,8 +141,7 @@ void launch_crc_stream(const CrcParams& p, uint32_t n, size_t max_file_bytes, cu
 {
     const uint32_t max_ctas = (uint32_t)((max_file_bytes / 4 + kCs2CtaWords - 1) / kCs2CtaWords) + 1u;
     dim3 grid(max_ctas, n);
-    FPNGB_SET_SMEM(idat_crc_stream_kernel, 32768);
-    idat_crc_stream_kernel<<<grid, 32 * kCs2Warps, 32768, s>>>(p);
+    idat_crc_stream_kernel<<<grid, 32 * kCs2Warps, 0, s>>>(p);
 }
 
 }  // namespace fpngb
