@@ -292,6 +292,7 @@ def run_ours(args, wl):
     if args.encoder != "default":
         L.fpngb_debug_use_fused(1 if args.encoder == "fused" else 0)
         L.fpngb_debug_crc_overlap(1 if args.encoder == "two_kernel" else 0)
+        L.fpngb_debug_pack_crc(0 if args.encoder == "two_kernel_file_crc" else 1)
     L.fpngb_profile_enable.argtypes = [C.c_int]
     L.fpngb_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int]
 
@@ -395,7 +396,8 @@ def run_ours(args, wl):
                         "(BASELINE config 2), --gpus N>1 to C3 (config 3): compare with `--gpus 1 --workload c3` (profiles/README.md) for the same-workload N=1 value",
         "kernels_ms": kern, "roofline": roof(dominant), "roofline_scan": roof("fused" if fused_path else "scan"),
         "encoder": "single-pass fused kernel (encode_fused.cu: filter + match + code emission + bit placement in one read of the pixels)" if fused_path
-                   else "two-kernel scan + pack",
+                   else "two-kernel scan + pack" + (" (IDAT CRC by the file-reading kernel)" if args.encoder == "two_kernel_file_crc" else
+                                                   " (scanline CRCs computed by the pack kernel on the staged code words; kernels_ms.crc is the combine kernel)"),
         "kernels_ms_sum": float(sum(kern.values())),
         "whole_step": {"algorithmic_gbs": (in_bytes + out_bytes) / 1e9 / (ms / args.steps / 1e3),
                        "frac_of_peak": (in_bytes + out_bytes) / 1e9 / (ms / args.steps / 1e3) / peak},
@@ -634,8 +636,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
-    ap.add_argument("--encoder", default="default", choices=["default", "two_kernel", "two_kernel_serial", "fused"],
-                    help="default: the library's choice; two_kernel: scan+pack with the chunked CRC overlap; two_kernel_serial: scan+pack, serial; fused: single-pass encoder")
+    ap.add_argument("--encoder", default="default", choices=["default", "two_kernel", "two_kernel_serial", "two_kernel_file_crc", "fused"],
+                    help="default: the library's choice; two_kernel: scan+pack with the chunked CRC overlap; two_kernel_serial: scan+pack, serial; two_kernel_file_crc: scan+pack, IDAT CRC by the file-reading kernel instead of the pack kernel; fused: single-pass encoder")
     ap.add_argument("--own-files", action="store_true", help="decode leg: use the GPU-written files instead of reference-written ones")
     args = ap.parse_args()
     if args.workload == "auto":

@@ -58,5 +58,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defs: str) -> str:
+    """Developer A/B builds: the same sources with extra -D macros, into fpng_b200/_variants/libfpng_b200_<name>.so
+    (loaded instead of the product library when FPNGB_LIB_VARIANT=<name>; never built or used by default)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(CSRC, "_obj_" + name)
+    vdir = os.path.join(PKG, "_variants")
+    os.makedirs(objdir, exist_ok=True)
+    os.makedirs(vdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + defs.split()
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        subprocess.check_call([nvcc] + cflags + ["-c", "-o", obj, src], cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    out = os.path.join(vdir, f"libfpng_b200_{name}.so")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-o", out + ".building"] + objs + LINK_FLAGS, cwd=CSRC)
+    os.replace(out + ".building", out)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

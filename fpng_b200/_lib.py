@@ -17,6 +17,11 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB
+    variant = os.environ.get("FPNGB_LIB_VARIANT")            # developer A/B builds (_build.build_variant); must exist
+    if variant:
+        path = os.path.join(_build.PKG, "_variants", f"libfpng_b200_{variant}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
     if not os.path.exists(path):
         # On a dev box without the prebuilt .so: compile it (needs nvcc); never substitute another implementation.
         _build.build()

@@ -14,6 +14,7 @@
 // About 3.3 thread-instructions per byte (4 table look-ups + 8 address instructions + 3 XORs per word).
 #include "kernels.cuh"
 #include "crc_math.cuh"
+#include <algorithm>
 
 namespace fpngb {
 
@@ -27,6 +28,7 @@ __device__ uint32_t g2_byte[256];                 // plain byte table (tail byte
 __device__ uint32_t g2_lane_mul[32][8][16];       // multiply by x^(32 * (32 - lane))
 __device__ uint32_t g2_warp_mul[kCs2Warps][8][16];   // multiply by x^(32 * kCs2WarpWords * m)
 __constant__ uint32_t c2_xpow2[64];               // x^(2^k)
+__device__ uint32_t g2_xpow8[4][256];             // x^(8 * d * 256^k): powers of x by byte digits of the byte distance
 
 int crc_stream_tables_init()
 {
@@ -49,6 +51,18 @@ int crc_stream_tables_init()
     FPNGB_CUDA_OK(cudaMemcpyToSymbol(g2_lane_mul, lane, sizeof lane));
     FPNGB_CUDA_OK(cudaMemcpyToSymbol(g2_warp_mul, wm, sizeof wm));
     FPNGB_CUDA_OK(cudaMemcpyToSymbol(c2_xpow2, xp, sizeof xp));
+    static uint32_t p8[4][256];
+    for (int k = 0; k < 4; k++) for (unsigned long long d = 0; d < 256; d++) p8[k][d] = xpow(8ull * (d << (8 * k)));
+    FPNGB_CUDA_OK(cudaMemcpyToSymbol(g2_xpow8, p8, sizeof p8));
+    return 0;
+}
+
+int crc_stream_table_ptrs(const uint32_t** f128b, const uint32_t** lane_mul)
+{
+    void *a = nullptr, *b = nullptr;
+    FPNGB_CUDA_OK(cudaGetSymbolAddress(&a, g2_f128b));
+    FPNGB_CUDA_OK(cudaGetSymbolAddress(&b, g2_lane_mul));
+    *f128b = (const uint32_t*)a; *lane_mul = (const uint32_t*)b;
     return 0;
 }
 
@@ -135,6 +149,95 @@ __global__ void __launch_bounds__(32 * kCs2Warps) idat_crc_stream_kernel(CrcPara
             q[0] = (uint8_t)(reg >> 24); q[1] = (uint8_t)(reg >> 16); q[2] = (uint8_t)(reg >> 8); q[3] = (uint8_t)reg;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// IDAT CRC from the scanline CRCs of the 16-pixel pack kernel (encode16_kernels.cu): the file is never read back.
+//
+// The CRC is GF(2)-linear in the message BITS and Deflate packs bits LSB-first, the order the reflected CRC consumes them,
+// so the message splits into bit strings whose zero-initialised CRCs are shifted to the end of the message and XOR-ed:
+//      "IDAT" + block header | scanline 0 | ... | scanline h-1 | end-of-block code | Adler-32
+// A scanline's value R covers its code words at their true word alignment in the file (zero outside its own bits) up to
+// word B = ((G + bits) >> 5) + 1: contribution R * x^(E - 32 B), E = end of the message in bits.
+// grid (kRowCrcSplit, n): each CTA takes a slice of the image's scanlines; the last CTA of an image adds the fixed parts,
+// the initial value and the final XOR (both linear as well) and stores the CRC.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kRowCrcThreads = 256, kRowCrcSplit = 8;
+
+__device__ __forceinline__ uint32_t crc_bits(uint32_t reg, uint32_t v, uint32_t nbits)
+{
+    for (uint32_t i = 0; i < nbits; i++) { reg = (reg >> 1) ^ (((reg ^ (v >> i)) & 1u) ? kCrcPoly : 0u); }
+    return reg;
+}
+
+// x^e from byte-digit tables: x^e = x^(e & 7) * prod_k g2_xpow8[k][digit k of e >> 3]  (e < 2^35: every file this library writes)
+__device__ __forceinline__ uint32_t xpow_tab(unsigned long long e)
+{
+    uint32_t r = kCrcOne >> (uint32_t)(e & 7ull);
+    uint32_t d = (uint32_t)(e >> 3);
+#pragma unroll 1
+    for (int k = 0; d; k++, d >>= 8)
+        if (d & 0xFFu) r = gf2_mulmod(r, g2_xpow8[k][d & 0xFFu]);
+    return r;
+}
+
+__global__ void __launch_bounds__(kRowCrcThreads) row_crc_combine_kernel(RowCrcParams p)
+{
+    __shared__ uint32_t s_part[kRowCrcThreads / 32];
+    const uint32_t img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    ImageState* st = p.st + img;
+    if (st->stored) return;                                                  // stored-block images: idat_crc_stream_kernel reads the file
+    const CodeBook* book = p.books + (size_t)img * p.book_stride;
+    const unsigned long long E = (unsigned long long)(kPngHeaderSize + st->zsize) * 8ull;
+    const size_t r0 = (size_t)img * p.h;
+    uint32_t acc = 0;
+    for (uint32_t y = blockIdx.x * kRowCrcThreads + tid; y < p.h; y += kRowCrcThreads * gridDim.x) {
+        const unsigned long long B = ((p.row_ofs[r0 + y] + p.row_bits[r0 + y]) >> 5) + 1ull;
+        acc ^= gf2_mulmod(p.row_crc[r0 + y], xpow_tab(E - 32ull * B));
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        // the fixed parts, one 32-bit piece per thread: block header words, "IDAT", end-of-block code, Adler-32, initial value
+        const uint32_t hb = book->hdr_bits, nhw = (hb + 31u) >> 5;
+        if (tid < nhw) {
+            const uint32_t nb = min(32u, hb - 32u * tid);
+            uint32_t v = 0;
+            for (uint32_t i = 0; i < (nb + 7u) >> 3; i++) v |= (uint32_t)book->hdr[4u * tid + i] << (8u * i);
+            acc ^= gf2_mulmod(crc_bits(0u, v, nb), xpow_tab(E - ((unsigned long long)kZlibBitBase + 32ull * tid + nb)));
+        } else if (tid == kRowCrcThreads - 1) {
+            acc ^= gf2_mulmod(crc_bits(0u, 0x54414449u, 32), xpow_tab(E - (unsigned long long)kZlibBitBase));   // 'I' 'D' 'A' 'T', first byte in the low bits
+        } else if (tid == kRowCrcThreads - 2) {
+            const unsigned long long e = p.row_ofs[r0 + p.h - 1] + p.row_bits[r0 + p.h - 1];   // end-of-block code right after the last scanline
+            const uint32_t eob_bits = book->eob >> 16;
+            acc ^= gf2_mulmod(crc_bits(0u, book->eob & 0xFFFFu, eob_bits), xpow_tab(E - e - eob_bits));
+        } else if (tid == kRowCrcThreads - 3) {
+            acc ^= crc_bits(0u, __byte_perm(st->adler, 0u, 0x0123), 32);    // Adler-32, big-endian, the last four bytes of the message
+        } else if (tid == kRowCrcThreads - 4) {
+            acc ^= gf2_mulmod(0xFFFFFFFFu, xpow_tab(E - 8ull * (kPngHeaderSize - 4u))) ^ 0xFFFFFFFFu;   // initial value advanced over the message, final XOR
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        acc = 0;
+        for (uint32_t u = 0; u < kRowCrcThreads / 32; u++) acc ^= s_part[u];
+        atomicXor(&st->crc_acc, acc);
+        __threadfence();
+        const uint32_t done = atomicAdd(&st->tiles_done, 1u);
+        if (done == gridDim.x - 1) {
+            __threadfence();
+            const uint32_t crc = atomicXor(&st->crc_acc, 0u);
+            uint8_t* q = p.out + (size_t)img * p.out_stride + kPngHeaderSize + st->zsize;
+            q[0] = (uint8_t)(crc >> 24); q[1] = (uint8_t)(crc >> 16); q[2] = (uint8_t)(crc >> 8); q[3] = (uint8_t)crc;
+        }
+    }
+}
+
+void launch_row_crc_combine(const RowCrcParams& p, uint32_t n, cudaStream_t s)
+{
+    const uint32_t split = std::min(kRowCrcSplit, (p.h + kRowCrcThreads - 1) / kRowCrcThreads);
+    row_crc_combine_kernel<<<dim3(split, n), kRowCrcThreads, 0, s>>>(p);
 }
 
 void launch_crc_stream(const CrcParams& p, uint32_t n, size_t max_file_bytes, cudaStream_t s)

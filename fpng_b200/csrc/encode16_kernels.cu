@@ -7,7 +7,10 @@
 namespace fpngb {
 
 constexpr int kScan16Rows = 8;                   // warps (scanlines) per CTA, scan
-constexpr int kPack16Rows = 4;                   // warps per CTA, pack (larger staging buffers)
+#ifndef FPNGB_PACK_WARPS
+#define FPNGB_PACK_WARPS 7
+#endif
+constexpr int kPack16Rows = FPNGB_PACK_WARPS;    // warps per CTA, pack (larger staging buffers)
 constexpr uint32_t kRowsPerWarp16 = 5;           // consecutive scanlines per warp (pack kernel) on large batches: amortises the CTA prologue and
                                                  // lets a scanline's first tile be prefetched during the previous scanline's last step
 // small jobs (a single image) keep one scanline per warp so that the grid still fills the GPU
@@ -357,10 +360,12 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
 #endif
     uint32_t* s_match = s_lit + 512;
     uint32_t* s_stage_all = s_match + 88;
+    uint32_t* s_crc = s_stage_all + kPack16Rows * stage16_words<CHANS>();              // [4][256] CRC slice tables (row_crc only)
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t img = blockIdx.y;
     const uint32_t row0 = (blockIdx.x * kPack16Rows + warp) * rows_per_warp;           // this warp's first scanline
+    const bool do_crc = p.row_crc != nullptr;
     const CodeBook* book = p.books + (size_t)img * p.book_stride;
     const ImageState st = p.st[img];
     if (st.stored) {                             // stored-block fallback (fpng.cpp:818-866): strided copy of the rows
@@ -378,11 +383,16 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
 #endif
     }
     if (threadIdx.x < 88) s_match[threadIdx.x] = book->match[threadIdx.x];
+    if (do_crc) for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_crc[i] = __ldg(p.crc_f128b + i);
     __syncthreads();
     if (row0 >= p.h) return;
 
     const uint32_t w = p.w, bpl = w * CHANS;
     const uint32_t nrows = min(rows_per_warp, p.h - row0);
+    const uint32_t crc_s = smem_u32(s_crc);
+    // CRC of the scanline's code words (PackParams::row_crc): lane l owns the words whose index in the scanline is l (mod 32),
+    // a Horner recurrence over 128-byte strides; cx is the register XOR-ed with the lane's latest word, not yet advanced
+    uint32_t cx = 0;
     const uint8_t* img_px = p.pixels + (size_t)img * p.image_stride;
     uint32_t* stage = s_stage_all + warp * stage16_words<CHANS>();
     const uint32_t stage_s = smem_u32(stage), lit_s = smem_u32(s_lit), match_s = smem_u32(s_match);
@@ -533,10 +543,14 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
 
         // ---- flush the complete words; carry the partial one in a register
         leftover = stage[nwords];
-        for (uint32_t j = lane; j < nwords; j += 32) {
+        // lanes take the words in scanline order rotated by the words already flushed, so that a lane always sees stride 32
+        for (uint32_t j = (lane - (flushed_bits >> 5)) & 31u; j < nwords; j += 32) {
             const uint32_t v = stage[j];
             if (first_pending && j == 0) atomicOr(gptr, v);
             else gptr[j] = v;
+            if (do_crc)
+                cx = v ^ lds_u32(crc_s + ((cx & 0xFFu) << 2)) ^ lds_u32(crc_s + 1024u + ((cx >> 6) & 0x3FCu)) ^
+                     lds_u32(crc_s + 2048u + ((cx >> 14) & 0x3FCu)) ^ lds_u32(crc_s + 3072u + ((cx >> 22) & 0x3FCu));
         }
         __syncwarp();                                                    // staging is rewritten by the next step
         if (nwords) first_pending = false;
@@ -545,6 +559,21 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         if (more) step++;
         else {                                                           // end of the scanline: its last, partial word
             if (lane == 0 && leftover) atomicOr(gptr, leftover);
+            if (do_crc) {
+                // the partial word (possibly empty) counts as word Wn; every lane's value is shifted to the end of word Wn
+                const uint32_t Wn = flushed_bits >> 5;
+                if (lane == (Wn & 31u))
+                    cx = leftover ^ lds_u32(crc_s + ((cx & 0xFFu) << 2)) ^ lds_u32(crc_s + 1024u + ((cx >> 6) & 0x3FCu)) ^
+                         lds_u32(crc_s + 2048u + ((cx >> 14) & 0x3FCu)) ^ lds_u32(crc_s + 3072u + ((cx >> 22) & 0x3FCu));
+                const uint32_t* lm = p.crc_lane_mul + (31u - ((Wn - lane) & 31u)) * 128u;    // x^(32 * (words after the lane's last + 1))
+                uint32_t r = __ldg(lm + (cx & 15u));
+#pragma unroll
+                for (int t = 1; t < 8; t++) r ^= __ldg(lm + 16 * t + ((cx >> (4 * t)) & 15u));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) r ^= __shfl_xor_sync(kFullMask, r, o);
+                if (lane == 0) p.row_crc[ridx0 + r_i] = r;
+                cx = 0;
+            }
             step = 0; r_i++;
         }
     }
@@ -562,7 +591,7 @@ bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t
 template <int CHANS, bool DIRECT> constexpr size_t scan16_smem() { return kScan16Rows * Loader16<CHANS, DIRECT>::type::kWarpBytes + 256 + 96; }
 template <int CHANS, bool DIRECT> constexpr size_t pack16_smem()
 {
-    return kPack16Rows * Loader16<CHANS, DIRECT>::type::kWarpBytes + ((FPNGB_PACK_LIT64 ? 1024 : 0) + 512 + 88 + kPack16Rows * stage16_words<CHANS>()) * 4;
+    return kPack16Rows * Loader16<CHANS, DIRECT>::type::kWarpBytes + ((FPNGB_PACK_LIT64 ? 1024 : 0) + 512 + 88 + kPack16Rows * stage16_words<CHANS>() + 1024) * 4;
 }
 template <int CHANS, bool DIRECT> constexpr size_t hist16_smem() { return kScan16Rows * Loader16<CHANS, DIRECT>::type::kWarpBytes + kScan16Rows * 288 * 4; }
 

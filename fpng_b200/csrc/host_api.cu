@@ -24,6 +24,7 @@ namespace fpngb {
 
 static std::atomic<uint64_t> g_launches{0};
 
+static bool g_pack_crc = true;                  // fpngb_debug_pack_crc(): the 16-pixel pack kernel computes scanline CRCs (no CRC pass over the file)
 static bool g_inline_crc = true;                // fpngb_debug_inline_crc(): the single-pass encoder computes the IDAT CRC from in-kernel partials
 static bool g_crc_stream = true;                // fpngb_debug_crc_stream(0): first-generation (tile-staging) IDAT CRC kernel
 static int g_fused_mode = -1;                   // fpngb_debug_use_fused(): 1 single-pass encoder, 0 two-kernel encoder, -1 environment (FPNGB_FUSED)
@@ -184,6 +185,7 @@ struct Workspace {
     uint32_t* row_bits; uint2* row_adler; unsigned long long* row_ofs; ImageState* st; uint32_t* hist; CodeBook* books;
     uint2* lane_ofs; uint32_t lane_ofs_pitch;
     void* fused_desc;
+    uint32_t* row_crc;
 };
 
 
@@ -200,9 +202,11 @@ static int carve_workspace(Context& c, uint32_t n, uint32_t h, uint32_t width, b
     const size_t o_books = o; o = align_up(o + (two_pass ? (size_t)n * sizeof(CodeBook) : 0), 256);
     const size_t o_lane = o; o = align_up(o + (fused ? 0 : rows * lane_pitch * 8), 256);
     const size_t o_desc = o; o = align_up(o + (fused ? fused_desc_bytes(n, width, h) : 0), 256);
+    const size_t o_rcrc = o; o = align_up(o + (fused ? 0 : rows * 4), 256);
     int rc = c.ws.reserve(o);
     if (rc) return rc;
     uint8_t* b = (uint8_t*)c.ws.p;
+    w.row_crc = (uint32_t*)(b + o_rcrc);
     w.row_bits = (uint32_t*)(b + o_bits); w.row_adler = (uint2*)(b + o_adl); w.row_ofs = (unsigned long long*)(b + o_ofs);
     w.st = (ImageState*)(b + o_st); w.hist = (uint32_t*)(b + o_hist); w.books = (CodeBook*)(b + o_books);
     w.lane_ofs = (uint2*)(b + o_lane); w.lane_ofs_pitch = lane_pitch;
@@ -326,6 +330,9 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
         pp.row_ofs = ws.row_ofs + r0; pp.row_bits = sp.row_bits; pp.lane_ofs = sp.lane_ofs; pp.lane_ofs_pitch = ws.lane_ofs_pitch;
         pp.row_adler = sp.row_adler; pp.st = sp.st; pp.out = out; pp.out_stride = out_stride;
         pp.lit1_rule = lit1_rule;
+        // the 16-pixel pack kernel computes each scanline's CRC while its code words are staged; the file is not read back
+        const bool pack_crc = v2 && !fused && g_pack_crc;
+        if (pack_crc) { pp.row_crc = ws.row_crc + r0; pp.crc_f128b = c.crc_f128b; pp.crc_lane_mul = c.crc_lane_mul; }
         if (fused) {
             cudaEvent_t mid = ps ? ps->ev[kProfFused + 1] : nullptr;
             rc = launch_encode_fused(px, image_stride, cnt, w, h, chans, flags, books, book_stride, sp.row_adler, sp.st, ws.fused_desc,
@@ -367,6 +374,12 @@ static int encode_batch_locked(Context& c, const uint8_t* d_pixels, size_t image
         if (fused && g_inline_crc) {
             launch_fused_crc(ws.fused_desc, cnt, w, h, books, book_stride, sp.st, out, out_stride, cs);   // combine the in-kernel partials
             cp.stored_only = 1u;                                              // the file-reading CRC kernel is only needed for stored-block images
+            count_launch(1);
+        }
+        if (pack_crc) {
+            RowCrcParams rp{pp.row_crc, pp.row_ofs, pp.row_bits, books, book_stride, sp.st, out, out_stride, h};
+            launch_row_crc_combine(rp, cnt, cs);
+            cp.stored_only = 1u;
             count_launch(1);
         }
         if (g_crc_stream) launch_crc_stream(cp, cnt, max_encoded_size(w, h, chans), cs); else launch_crc(cp, cnt, cs);
@@ -412,6 +425,8 @@ int fpngb_init(int device)
     if (rc) return rc;
     rc = crc_stream_tables_init();
     if (rc) return rc;
+    rc = crc_stream_table_ptrs(&c.crc_f128b, &c.crc_lane_mul);
+    if (rc) return rc;
     c.pin_small.pinned = true;
     rc = c.pin_small.reserve(1 << 16);
     if (rc) return rc;
@@ -434,6 +449,8 @@ FPNGB_API void fpngb_debug_use_fused(int mode) { g_fused_mode = mode; }
 FPNGB_API void fpngb_debug_crc_overlap(int on) { g_crc_overlap = on != 0; }
 FPNGB_API void fpngb_debug_crc_stream(int on) { g_crc_stream = on != 0; }
 FPNGB_API void fpngb_debug_inline_crc(int on) { g_inline_crc = on != 0; }
+// test hook: 0 = the two-kernel encoder leaves the IDAT CRC to the file-reading CRC kernel instead of computing it in the pack kernel
+FPNGB_API void fpngb_debug_pack_crc(int on) { g_pack_crc = on != 0; }
 
 // exposes the static code books to the tests (sizes[288], codes[288]); not part of the reference surface
 FPNGB_API int fpngb_debug_static_table(uint32_t chans, uint8_t* sizes, uint16_t* codes, uint32_t* hdr_bits)

@@ -44,6 +44,19 @@ struct PackParams {
     uint8_t* out; size_t out_stride;
     uint32_t lit1_rule;                           // see ScanParams
     uint32_t stored_only;                         // 16-pixel pack kernel: only write images that fell back to stored blocks (fused encoder ran before)
+    // 16-pixel pack kernel: raw CRC-32 of each scanline's code words, computed while they sit in the staging buffer
+    // (nullptr = off; the file-reading CRC kernel runs instead).  Tables: crc_stream_kernel.cu.
+    uint32_t* row_crc;                            // [n*h]
+    const uint32_t* crc_f128b;                    // [4][256] slice tables of the 128-byte advance
+    const uint32_t* crc_lane_mul;                 // [32][8][16] nibble tables of x^(32 * (32 - l))
+};
+
+// combines the scanline CRCs of the pack kernel into the IDAT CRC (crc_stream_kernel.cu)
+struct RowCrcParams {
+    const uint32_t* row_crc; const unsigned long long* row_ofs; const uint32_t* row_bits;
+    const CodeBook* books; uint32_t book_stride;
+    ImageState* st; uint8_t* out; size_t out_stride;
+    uint32_t h;
 };
 
 struct AdlerParams {
@@ -85,6 +98,8 @@ int fused_tables_init();
 // second-generation IDAT CRC kernel (crc_stream_kernel.cu)
 int crc_stream_tables_init();
 void launch_crc_stream(const CrcParams& p, uint32_t n, size_t max_file_bytes, cudaStream_t s);
+void launch_row_crc_combine(const RowCrcParams& p, uint32_t n, cudaStream_t s);
+int crc_stream_table_ptrs(const uint32_t** f128b, const uint32_t** lane_mul);
 
 void launch_scan(const ScanParams& p, uint32_t n, uint32_t chans, int mode, bool hist, cudaStream_t s);
 bool walk16_eligible(const void* base, size_t image_stride, uint32_t w, uint32_t chans);

@@ -24,6 +24,8 @@ struct Context {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the pipelined host batch path
     cudaStream_t side = nullptr;                 // CRC kernels of one chunk run here underneath the scan/pack kernels of the next
     cudaEvent_t side_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const uint32_t* crc_f128b = nullptr;        // device tables of the in-kernel CRC (crc_stream_kernel.cu)
+    const uint32_t* crc_lane_mul = nullptr;
     CodeBook* d_static_books = nullptr;          // [0] RGB, [1] RGBA
     CodeBook h_static_books[2];
     Buffer ws;                                    // kernel workspace (row tables, image state, histograms, books)

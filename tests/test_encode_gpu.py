@@ -248,16 +248,18 @@ def test_random_dimension_fuzz_like_reference_E(gpu, oracle):
                 assert st == 0
 
 
-@pytest.mark.parametrize("mode", ["fused+inline_crc", "fused", "two_kernel", "two_kernel_serial_crc"])
+@pytest.mark.parametrize("mode", ["fused+inline_crc", "fused", "two_kernel", "two_kernel_chunked", "two_kernel_file_crc", "two_kernel_file_crc_chunked"])
 def test_encoder_generations_agree_with_oracle(gpu, oracle, mode):
     """The single-pass encoder (encode_fused.cu: decoupled look-back, lane-local bit strings, in-kernel CRC partials), the same
-    with the file-reading CRC kernel, and the two-kernel scan + pack encoder must all write the reference's bytes."""
+    with the file-reading CRC kernel, and the two-kernel scan + pack encoder (default: scanline CRCs from the pack kernel; with the
+    file-reading CRC kernel; each also cut into chunks with the CRC work on a side stream) must all write the reference's bytes."""
     import torch
     from fpng_b200._lib import lib
     L = lib()
     L.fpngb_debug_inline_crc(1 if mode == "fused+inline_crc" else 0)
     L.fpngb_debug_use_fused(1 if mode.startswith("fused") else 0)
-    L.fpngb_debug_crc_overlap(0 if mode == "two_kernel_serial_crc" else 1)
+    L.fpngb_debug_crc_overlap(1 if mode.endswith("_chunked") else 0)
+    L.fpngb_debug_pack_crc(0 if "file_crc" in mode else 1)
     try:
         # aligned and unaligned scanlines (the single-pass kernel has a staged-tile and a direct-load variant), partial units,
         # widths beyond its reach (> 4096: two-kernel encoder), one-pixel and one-row images
@@ -279,7 +281,8 @@ def test_encoder_generations_agree_with_oracle(gpu, oracle, mode):
     finally:
         L.fpngb_debug_inline_crc(1)
         L.fpngb_debug_use_fused(-1)
-        L.fpngb_debug_crc_overlap(1)
+        L.fpngb_debug_crc_overlap(0)
+        L.fpngb_debug_pack_crc(1)
 
 
 def test_single_pass_encoder_many_groups(gpu, ref):
