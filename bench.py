@@ -362,7 +362,9 @@ def run_ours(args, wl):
     peak, peak_src = measured_peak()
     fused_path = kern["fused"] > 0
     algo = {"hist": in_bytes, "huffman": 0, "scan": in_bytes, "offsets": 0, "fused": in_bytes + out_bytes, "finish": 0,
-            "pack": 0 if fused_path else in_bytes + out_bytes, "adler": 0, "crc": out_bytes}
+            "pack": 0 if fused_path else in_bytes + out_bytes, "adler": 0,
+            # default encoder: the pack kernel computes the scanline CRCs, kernels_ms.crc is the small combine kernel (no file bytes read)
+            "crc": out_bytes if (fused_path or args.encoder == "two_kernel_file_crc") else 0}
     dominant = max(kern, key=lambda k: kern[k])
 
     # DRAM traffic per launch from the committed `ncu --set full` capture of the same workload (profiles/traffic.json,

@@ -29,11 +29,14 @@ struct DecodeState {
     unsigned long long end_byte;            // bytes consumed up to and including the padded EOB
 };
 
+constexpr uint32_t kFastWords = 4096 + 64;   // 4096 fast entries, then the 256 literal code sizes (bytes)
+
 struct DecodeParams {
     const uint8_t* d_files; size_t file_stride;
     const FileDesc* files;                  // [n] device
     DecodeState* state;                     // [n]
     uint32_t* luts;                         // [n][4096]  fused entries, see decode_kernels.cu
+    uint32_t* fast;                         // [n][kFastWords]  multi-token entries + literal code sizes of the scan / write loops
     SubInfo* subs; uint32_t subs_per_file;  // [n][subs_per_file]
     uint8_t* delta; uint32_t delta_pitch;   // [n][h][pitch] filtered rows without the filter byte
     uint8_t* d_out; size_t out_stride;

@@ -73,6 +73,7 @@ static int decode_batch_locked(const uint8_t* d_files, size_t file_stride, const
     const size_t o_files = o; o = align_up(o + (size_t)n * sizeof(FileDesc), 256);
     const size_t o_state = o; o = align_up(o + (size_t)n * sizeof(DecodeState), 256);
     const size_t o_luts = o; o = align_up(o + (size_t)n * 4096 * 4, 256);
+    const size_t o_fast = o; o = align_up(o + (size_t)n * kFastWords * 4, 256);
     uint32_t max_idat = 0;
     for (uint32_t i = 0; i < n; i++) if (h_files[i].idat_len > max_idat) max_idat = h_files[i].idat_len;
     const uint32_t subs_per_file = (uint32_t)(((uint64_t)max_idat * 8 + 32) / kSubBits + 2);
@@ -92,7 +93,7 @@ static int decode_batch_locked(const uint8_t* d_files, size_t file_stride, const
     FPNGB_CUDA_OK(cudaEventRecord(staged, s));
     DecodeParams p{};
     p.d_files = d_files; p.file_stride = file_stride; p.files = (const FileDesc*)(b + o_files); p.state = (DecodeState*)(b + o_state);
-    p.luts = (uint32_t*)(b + o_luts); p.subs = (SubInfo*)(b + o_subs); p.subs_per_file = subs_per_file; p.delta = b + o_delta; p.delta_pitch = pitch; p.d_out = d_out; p.out_stride = out_stride;
+    p.luts = (uint32_t*)(b + o_luts); p.fast = (uint32_t*)(b + o_fast); p.subs = (SubInfo*)(b + o_subs); p.subs_per_file = subs_per_file; p.delta = b + o_delta; p.delta_pitch = pitch; p.d_out = d_out; p.out_stride = out_stride;
     p.d_status = d_status; p.w = w; p.h = h; p.chans = chans;
     launch_decode(p, n, desired, s);
     count_launch(8);

@@ -189,6 +189,32 @@ __global__ void __launch_bounds__(32) decode_prepare_kernel(DecodeParams p)
         }
         lut[i] = e;
     }
+    // Fast table of the scan / write loops (one shared-memory look-up per 12 stream bits, one uniform code path):
+    //   bits 0..3  L     stream bits consumed by the whole entry (0: not fast -- end of block, invalid code, a match whose
+    //                    code + extra bits + distance bit do not fit in the 12 index bits; the loops fall back to `lut`)
+    //   bits 4..5  cnt   number of literals (1..3), 0 = one match
+    //   bits 8..31       the literals, first one in the low byte / the match's run length in bytes
+    // followed by the 256 literal code sizes (the loops split a multi-literal entry at a subsequence boundary with them).
+    uint32_t* fast = p.fast + (size_t)f * kFastWords;
+    for (uint32_t i = lane; i < 4096; i += 32) {
+        const uint32_t e0 = s_base[i], sym0 = e0 & 511u, len0 = e0 >> 9;
+        uint32_t fe = 0;
+        if (len0 && sym0 < 256u) {
+            uint32_t L = len0, cnt = 1, P = sym0;
+            for (uint32_t k = 1; k < 3; k++) {
+                const uint32_t e1 = s_base[i >> L], sym1 = e1 & 511u, len1 = e1 >> 9;
+                if (!len1 || sym1 >= 256u || L + len1 > 12u) break;
+                P |= sym1 << (8u * k); L += len1; cnt++;
+            }
+            fe = L | (cnt << 4) | (P << 8);
+        } else if (len0 && sym0 > 256u && sym0 <= 285u) {
+            const uint32_t xb = c_len_xbits[sym0 - 257u];
+            if (len0 + xb + 1u <= 12u) fe = (len0 + xb + 1u) | ((c_len_base[sym0 - 257u] + ((i >> len0) & ((1u << xb) - 1u))) << 8);
+        }
+        fast[i] = fe;
+    }
+    for (uint32_t i = lane; i < 64; i += 32)
+        fast[4096 + i] = s_sizes[4 * i] | (s_sizes[4 * i + 1] << 8) | (s_sizes[4 * i + 2] << 16) | ((uint32_t)s_sizes[4 * i + 3] << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -229,6 +255,15 @@ constexpr uint32_t kWinLead = 8, kWinTail = 8;                                  
 constexpr uint32_t kWinWords = kWinLead + kDecThreads * (kSubBits / 32) + kWinTail;
 constexpr uint32_t kWinSmemWords = kWinWords + kWinWords / 32 + 1;
 
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16g(uint32_t* smem_dst, const uint32_t* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
 // cooperative load of the CTA's stream window; `first_sub` = index of the CTA's first subsequence
 __device__ __forceinline__ void stage_window(Stream& st, uint32_t* s_win, unsigned long long first_sub)
 {
@@ -236,12 +271,25 @@ __device__ __forceinline__ void stage_window(Stream& st, uint32_t* s_win, unsign
     const uint32_t base = (uint32_t)(w0 >= kWinLead ? w0 - kWinLead : 0ull);
     // word i lives at s_win[i + i / 32]; the pad slot in front of every 32-word block holds a COPY of the block's first word, so
     // that (address, address + 1) always are two consecutive stream words (win_peek below reads 32 bits at any bit position)
+    // asynchronous copies (LDGSTS): all of a thread's ~33 words are in flight at once instead of one load -> store round trip each
+    // (ncu: a quarter of the scan kernel's stall samples sat on the staging stores); the caller waits with stage_wait()
     for (uint32_t i = threadIdx.x; i < kWinWords; i += blockDim.x) {
-        const uint32_t v = __ldg(st.words + min(base + i, st.max_widx));
-        s_win[i + (i >> 5)] = v;
-        if ((i & 31u) == 0u && i) s_win[i + (i >> 5) - 1u] = v;
+        const uint32_t* src = st.words + min(base + i, st.max_widx);
+        cp_async4(s_win + i + (i >> 5), src);
+        if ((i & 31u) == 0u && i) cp_async4(s_win + i + (i >> 5) - 1u, src);
     }
     st.swin = s_win; st.sw_base = base; st.sw_count = kWinWords;
+}
+
+// the file's fast table (kFastWords words, 16-byte aligned) into shared memory, asynchronously
+__device__ __forceinline__ void stage_fast_table(uint32_t* s_fast, const uint32_t* __restrict__ g_fast)
+{
+    for (uint32_t i = threadIdx.x; i < kFastWords / 4u; i += blockDim.x) cp_async16g(s_fast + 4u * i, g_fast + 4u * i);
+}
+__device__ __forceinline__ void stage_wait()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
 }
 
 __device__ __forceinline__ Stream open_stream(const uint8_t* file, const FileDesc& fd)
@@ -435,48 +483,73 @@ __device__ __forceinline__ uint32_t win_peek(const uint32_t* __restrict__ win, u
     return __funnelshift_r(win[a], win[a + 1u], q);                         // shift amount taken modulo 32
 }
 
+// One step of the fast loops: looks up the entry at bit position q of the window.  A multi-literal entry whose later
+// literals could start at or beyond `limit` (the subsequence boundary) is cut down to its first literal.  Returns false when
+// the entry is not fast (L = 0); then `w` still holds the 32 stream bits for the fall-back.
+struct FastTok { uint32_t L, cnt, payload, w; };
+__device__ __forceinline__ bool fast_tok(const uint32_t* __restrict__ win, const uint32_t* __restrict__ s_fast, uint32_t q, uint32_t rel, uint32_t limit, FastTok& t)
+{
+    t.w = win_peek(win, q);
+    const uint32_t e = s_fast[t.w & 4095u];
+    t.L = e & 15u; t.cnt = (e >> 4) & 3u; t.payload = e >> 8;
+    if (t.cnt >= 2u && rel + 12u > limit) {
+        t.payload &= 0xFFu; t.cnt = 1u;
+        t.L = reinterpret_cast<const uint8_t*>(s_fast + 4096)[t.payload];
+    }
+    return t.L != 0u;
+}
+
+// Fall-back of the fast loops: one token through the single-token table in global memory.  Returns the token's length in bits
+// (0 = invalid code), sets sym (256 = end of block) and, for a match, run.
+__device__ __forceinline__ uint32_t slow_tok(const uint32_t* __restrict__ lutg, uint32_t w, uint32_t& sym, uint32_t& run)
+{
+    const uint32_t e = __ldg(lutg + (w & 4095u));
+    const uint32_t l0 = lut_len0(e);
+    sym = lut_sym0(e); run = 0;
+    if (!l0 || sym > 285u) return 0u;
+    if (sym <= 256u) return l0;
+    const uint32_t xb = c_len_xbits[sym - 257u];
+    run = c_len_base[sym - 257u] + ((w >> l0) & ((1u << xb) - 1u));
+    return l0 + xb + 1u;                                                     // extra bits + the 1-bit distance code (fpng.cpp:2300)
+}
+
 // Scan pass on the window: same contract as decode_range<false>.  `O` = bit offset of abs_origin inside the window.
-__device__ __forceinline__ SubScan scan_window(const uint32_t* __restrict__ win, uint32_t O, const uint32_t* __restrict__ s_lut,
-                                               uint32_t rel, uint32_t lo, uint32_t hi)
+__device__ __forceinline__ SubScan scan_window(const uint32_t* __restrict__ win, uint32_t O, const uint32_t* __restrict__ s_fast,
+                                               const uint32_t* __restrict__ lutg, uint32_t rel, uint32_t lo, uint32_t hi)
 {
     SubScan r; r.first = lo; r.exit = 0; r.eob_end = 0; r.n_out = 0; r.nlit = 0; r.lits = 0;
+    FastTok t;
     while (rel < lo) {                                                       // pre-roll: lock on to the token grid
-        const uint32_t e = s_lut[win_peek(win, O + rel) & 4095u];
-        uint32_t l = lut_len0(e);
-        const uint32_t s = lut_sym0(e);
-        if (!l || s == 256u || s > 285u) { rel = lo; break; }
-        if (s > 256u) l += c_len_xbits[s - 257u] + 1u;
+        if (fast_tok(win, s_fast, O + rel, rel, lo, t)) { rel += t.L; continue; }
+        uint32_t sym, run;
+        const uint32_t l = slow_tok(lutg, t.w, sym, run);
+        if (!l || sym == 256u) { rel = lo; break; }                          // not locked on
         rel += l;
     }
     r.first = rel;
     uint32_t lits = 0, n_out = 0, nlit = 0;
     while (rel < hi) {
-        const uint32_t w = win_peek(win, O + rel);
-        const uint32_t e = s_lut[w & 4095u];
-        const uint32_t l0 = lut_len0(e), s = lut_sym0(e);
-        if (!l0) { r.exit = kRelErr; r.n_out = n_out; r.nlit = nlit; r.lits = lits; return r; }
-        if (s < 256u) {
-            const uint32_t l1 = lut_len1(e);
-            lits = (lits >> 8) | (s << 24);
-            if (l1 && (rel + l0 < hi)) { rel += l0 + l1; n_out += 2u; nlit += 2u; lits = (lits >> 8) | (lut_sym1(e) << 24); }
-            else { rel += l0; n_out += 1u; nlit += 1u; }
-        } else if (s == 256u) {
-            rel += l0;
-            r.exit = kRelEnd; r.eob_end = rel; r.n_out = n_out; r.nlit = nlit; r.lits = lits;
-            return r;
-        } else {
-            if (s > 285u) { r.exit = kRelErr; r.n_out = n_out; r.nlit = nlit; r.lits = lits; return r; }
-            const uint32_t xb = c_len_xbits[s - 257u];
-            n_out += c_len_base[s - 257u] + ((w >> l0) & ((1u << xb) - 1u));
-            rel += l0 + xb + 1u;                                             // extra bits + the 1-bit distance code (fpng.cpp:2300)
+        if (fast_tok(win, s_fast, O + rel, rel, hi, t)) {
+            rel += t.L;
+            n_out += t.cnt ? t.cnt : t.payload;
+            nlit += t.cnt;
+            lits = __funnelshift_r(lits, t.payload, 8u * t.cnt);              // the new literals enter at the top (cnt = 0: unchanged)
+            continue;
         }
+        uint32_t sym, run;
+        const uint32_t l = slow_tok(lutg, t.w, sym, run);
+        if (!l) { r.exit = kRelErr; r.n_out = n_out; r.nlit = nlit; r.lits = lits; return r; }
+        rel += l;
+        if (sym == 256u) { r.exit = kRelEnd; r.eob_end = rel; r.n_out = n_out; r.nlit = nlit; r.lits = lits; return r; }
+        if (sym < 256u) { n_out++; nlit++; lits = (lits >> 8) | (sym << 24); }   // (cannot happen: every literal is a fast entry)
+        else n_out += run;
     }
     r.exit = rel; r.n_out = n_out; r.nlit = nlit; r.lits = lits;
     return r;
 }
 
 template <int CHANS>
-__device__ __forceinline__ void decode_write_range(const Stream& st, const uint32_t* __restrict__ s_lut, unsigned long long abs_origin, uint32_t hi,
+__device__ __forceinline__ void decode_write_range(const Stream& st, const uint32_t* __restrict__ s_fast, const uint32_t* __restrict__ lutg, unsigned long long abs_origin, uint32_t hi,
                                                    uint8_t* __restrict__ delta, uint32_t pitch, uint32_t bpl, uint32_t h,
                                                    unsigned long long out_pos, uint32_t tail, uint32_t* err)
 {
@@ -490,6 +563,19 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
     uint32_t dcol = col0 ? col0 - 1u : 0u;             // data bytes of the current row already produced
     uint8_t* rowp = delta + (size_t)row * pitch;
     unsigned long long acc = 0; uint32_t nacc = 0;     // pending bytes: data columns [dcol - nacc, dcol), first one 4-byte aligned
+    // Completed words of the literal fast path wait in a 4-deep register queue (newest in q3) and leave as ONE 128-bit store once
+    // they fill a 16-byte aligned group: the write pass is bound by store transactions (every lane writes its own region, so a
+    // 32-bit store costs a whole L1 tag cycle per lane), not by decoding.  Every other path flushes the queue first.
+    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0, nq = 0;   // queued words: data columns [dcol - nacc - 4 nq, dcol - nacc)
+#define FPNGB_FLUSHQ() do { \
+        if (nq) { \
+            uint32_t* b__ = reinterpret_cast<uint32_t*>(rowp + dcol - nacc - 4u * nq); \
+            if (nq == 3u) { b__[0] = q1; b__[1] = q2; b__[2] = q3; } \
+            else if (nq == 2u) { b__[0] = q2; b__[1] = q3; } \
+            else b__[0] = q3; \
+            nq = 0u; \
+        } \
+    } while (0)
 
     // general byte sink: unaligned head bytes of the thread's range and a scanline's last bytes go out singly, everything else
     // as aligned 32-bit words
@@ -509,37 +595,48 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
         else { if (row >= h) { *err = 1; return; } FPNGB_EMIT(s__); } \
     } while (0)
 
+    FastTok t;
     while (rel < hi) {
-        const uint32_t w = win_peek(win, O + rel);
-        const uint32_t e = s_lut[w & 4095u];
-        const uint32_t l0 = lut_len0(e), s = lut_sym0(e);
-        if (!l0) return;                                                   // invalid code: the link pass already flagged it
-        if (s < 256u) {
-            const uint32_t l1 = lut_len1(e);
-            const bool two = l1 && (rel + l0 < hi);
-            const uint32_t cnt = two ? 2u : 1u;
-            rel += two ? l0 + l1 : l0;
-            // fast path (almost every literal): inside a scanline, the pending bytes word aligned -- append one or two bytes to the
-            // 64-bit accumulator, store a word when four are there; no per-byte branches
-            if (!need_filter && (nacc | ((dcol & 3u) == 0u)) && dcol + cnt < bpl && row < h) {
-                const uint32_t s1 = lut_sym1(e);
-                lits = (lits >> 8) | (s << 24);
-                uint32_t v = s;
-                if (two) { lits = (lits >> 8) | (s1 << 24); v |= s1 << 8; }
-                acc |= (unsigned long long)v << (8u * nacc);
-                nacc += cnt; dcol += cnt;
-                if (nacc >= 4u) { *reinterpret_cast<uint32_t*>(rowp + dcol - nacc) = (uint32_t)acc; acc >>= 32; nacc -= 4u; }
+        uint32_t run;
+        if (fast_tok(win, s_fast, O + rel, rel, hi, t)) {
+            rel += t.L;
+            if (t.cnt) {
+                const uint32_t cnt = t.cnt, P = t.payload;
+                // fast path (almost every literal): inside a scanline, the pending bytes word aligned -- append the one to three bytes
+                // to the 64-bit accumulator, store a word when four are there; no per-byte branches
+                if (!need_filter && (nacc | ((dcol & 3u) == 0u)) && dcol + cnt < bpl && row < h) {
+                    lits = __funnelshift_r(lits, P, 8u * cnt);
+                    acc |= (unsigned long long)P << (8u * nacc);
+                    nacc += cnt; dcol += cnt;
+                    if (nacc >= 4u) {
+                        const uint32_t wv = (uint32_t)acc;
+                        acc >>= 32; nacc -= 4u;
+                        const uint32_t wcol = dcol - nacc - 4u;              // data column of this word
+                        if (nq == 0u && (wcol & 15u)) *reinterpret_cast<uint32_t*>(rowp + wcol) = wv;   // not yet at a 16-byte boundary
+                        else {
+                            q0 = q1; q1 = q2; q2 = q3; q3 = wv;
+                            if (++nq == 4u) { *reinterpret_cast<uint4*>(rowp + wcol - 12u) = make_uint4(q0, q1, q2, q3); nq = 0u; }
+                        }
+                    }
+                    continue;
+                }
+                FPNGB_FLUSHQ();
+                FPNGB_LITERAL(P & 0xFFu);
+                if (cnt > 1u) FPNGB_LITERAL((P >> 8) & 0xFFu);
+                if (cnt > 2u) FPNGB_LITERAL(P >> 16);
                 continue;
             }
-            FPNGB_LITERAL(s);
-            if (two) FPNGB_LITERAL(lut_sym1(e));
-        } else if (s == 256u) {
-            break;
+            run = t.payload;
         } else {
-            if (s > 285u) return;
-            const uint32_t xb = c_len_xbits[s - 257u];
-            const uint32_t run = c_len_base[s - 257u] + ((w >> l0) & ((1u << xb) - 1u));
-            rel += l0 + xb + 1u;
+            uint32_t sym;
+            const uint32_t l = slow_tok(lutg, t.w, sym, run);
+            if (!l) return;                                                // invalid code: the link pass already flagged it
+            if (sym == 256u) break;
+            rel += l;
+            if (sym < 256u) { FPNGB_FLUSHQ(); FPNGB_LITERAL(sym); continue; }
+        }
+        {
+            FPNGB_FLUSHQ();
             const bool bad = row >= h || need_filter || dcol < (uint32_t)CHANS || (dcol % CHANS) != 0u || (run % CHANS) != 0u || dcol + run > bpl;
             if (bad) { *err = 1; return; }
             const uint32_t px = CHANS == 4 ? lits : (lits >> 8);          // last CHANS literals, oldest in the low byte
@@ -547,7 +644,11 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
                 // dcol % 4 == 0: nothing is pending, pixels are word aligned
                 uint32_t* d = reinterpret_cast<uint32_t*>(rowp + dcol);
                 const uint32_t npx = run >> 2;
-                for (uint32_t i = 0; i < npx; i++) d[i] = px;
+                uint32_t i = 0;
+                for (; i < npx && ((dcol + 4u * i) & 15u); i++) d[i] = px;             // up to the next 16-byte boundary
+                const uint4 px4 = make_uint4(px, px, px, px);
+                for (; i + 4u <= npx; i += 4u) *reinterpret_cast<uint4*>(d + i) = px4;
+                for (; i < npx; i++) d[i] = px;
                 dcol += run;
                 if (dcol == bpl) { row++; rowp += pitch; dcol = 0u; need_filter = true; }
             } else {
@@ -565,7 +666,13 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
                     }
                     const uint32_t nwords = left >> 2;
                     uint32_t* d = reinterpret_cast<uint32_t*>(rowp + dcol);
-                    for (uint32_t k = 0; k < nwords; k++) { d[k] = wa; const uint32_t t = wa; wa = wb; wb = wc; wc = t; }
+                    uint32_t k = 0;
+                    for (; k < nwords && ((dcol + 4u * k) & 15u); k++) { d[k] = wa; const uint32_t tw = wa; wa = wb; wb = wc; wc = tw; }
+                    for (; k + 4u <= nwords; k += 4u) {                       // four words advance the 3-word pattern by one
+                        *reinterpret_cast<uint4*>(d + k) = make_uint4(wa, wb, wc, wa);
+                        const uint32_t tw = wa; wa = wb; wb = wc; wc = tw;
+                    }
+                    for (; k < nwords; k++) { d[k] = wa; const uint32_t tw = wa; wa = wb; wb = wc; wc = tw; }
                     dcol += nwords << 2; left -= nwords << 2; ph = (ph + nwords) % 3u;      // 4 bytes advance the phase by 1
                     if (dcol == bpl) { row++; rowp += pitch; dcol = 0u; need_filter = true; }   // a run may end exactly at the end of its scanline
                 }
@@ -573,7 +680,9 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
             }
         }
     }
+    FPNGB_FLUSHQ();
     for (uint32_t i = 0; i < nacc; i++) rowp[dcol - nacc + i] = (uint8_t)(acc >> (8u * i));
+#undef FPNGB_FLUSHQ
 #undef FPNGB_EMIT
 #undef FPNGB_LITERAL
 }
@@ -603,8 +712,8 @@ __device__ __forceinline__ FileSpan file_span(const DecodeState& st, const Strea
 __global__ void __launch_bounds__(kDecThreads) decode_scan_kernel(DecodeParams p)
 {
     extern __shared__ __align__(16) uint32_t dec_smem[];
-    uint32_t* s_lut = dec_smem;                       // [4096]
-    uint32_t* s_win = dec_smem + 4096;                // [kWinSmemWords]
+    uint32_t* s_fast = dec_smem;                      // [kFastWords]
+    uint32_t* s_win = dec_smem + kFastWords;          // [kWinSmemWords]
     const uint32_t f = blockIdx.y, tid = threadIdx.x;
     const DecodeState st = p.state[f];
     if (st.status || st.stored) return;
@@ -613,20 +722,21 @@ __global__ void __launch_bounds__(kDecThreads) decode_scan_kernel(DecodeParams p
     const FileSpan sp = file_span(st, sm, fd);
     const unsigned long long g = sp.g0 + (unsigned long long)blockIdx.x * kDecThreads + tid;
     if (sp.g0 + (unsigned long long)blockIdx.x * kDecThreads > sp.g1) return;
-    for (uint32_t i = tid; i < 4096; i += blockDim.x) s_lut[i] = p.luts[(size_t)f * 4096 + i];
+    stage_fast_table(s_fast, p.fast + (size_t)f * kFastWords);
     stage_window(sm, s_win, sp.g0 + (unsigned long long)blockIdx.x * kDecThreads);
-    __syncthreads();
+    stage_wait();
     if (g > sp.g1) return;
+    const uint32_t* lutg = p.luts + (size_t)f * 4096;
     SubInfo* info = p.subs + (size_t)f * p.subs_per_file + (g - sp.g0);
     const unsigned long long lo_abs = g * kSubBits;
     SubScan r;
     unsigned long long origin;
     if (g == sp.g0) {            // the file's first subsequence starts exactly at the first token
         origin = sp.tok0;
-        r = scan_window(s_win, (uint32_t)(origin - 32ull * sm.sw_base), s_lut, 0u, 0u, (uint32_t)((g + 1) * kSubBits - origin));
+        r = scan_window(s_win, (uint32_t)(origin - 32ull * sm.sw_base), s_fast, lutg, 0u, 0u, (uint32_t)((g + 1) * kSubBits - origin));
     } else {
         origin = lo_abs - kPreRoll < sp.tok0 ? sp.tok0 : lo_abs - kPreRoll;     // never pre-roll across the block header
-        r = scan_window(s_win, (uint32_t)(origin - 32ull * sm.sw_base), s_lut, 0u, (uint32_t)(lo_abs - origin), (uint32_t)(lo_abs - origin) + kSubBits);
+        r = scan_window(s_win, (uint32_t)(origin - 32ull * sm.sw_base), s_fast, lutg, 0u, (uint32_t)(lo_abs - origin), (uint32_t)(lo_abs - origin) + kSubBits);
     }
     info->start = origin + r.first;
     info->exit = r.exit >= kRelErr ? (r.exit == kRelEnd ? kPosEnd : kPosErr) : origin + r.exit;
@@ -755,8 +865,8 @@ __global__ void __launch_bounds__(kLinkThreads) decode_link_kernel(DecodeParams 
 __global__ void __launch_bounds__(kDecThreads) decode_write_kernel(DecodeParams p)
 {
     extern __shared__ __align__(16) uint32_t dec_smem[];
-    uint32_t* s_lut = dec_smem;                       // [4096]
-    uint32_t* s_win = dec_smem + 4096;                // [kWinSmemWords]
+    uint32_t* s_fast = dec_smem;                      // [kFastWords]
+    uint32_t* s_win = dec_smem + kFastWords;          // [kWinSmemWords]
     const uint32_t f = blockIdx.y, tid = threadIdx.x;
     DecodeState* stp = p.state + f;
     if (stp->status || stp->stored) return;
@@ -764,9 +874,10 @@ __global__ void __launch_bounds__(kDecThreads) decode_write_kernel(DecodeParams 
     Stream sm = open_stream(p.d_files + (size_t)f * p.file_stride, fd);
     const FileSpan sp = file_span(*stp, sm, fd);
     if (sp.g0 + (unsigned long long)blockIdx.x * kDecThreads > sp.g1) return;
-    for (uint32_t i = tid; i < 4096; i += blockDim.x) s_lut[i] = p.luts[(size_t)f * 4096 + i];
+    stage_fast_table(s_fast, p.fast + (size_t)f * kFastWords);
     stage_window(sm, s_win, sp.g0 + (unsigned long long)blockIdx.x * kDecThreads);
-    __syncthreads();
+    stage_wait();
+    const uint32_t* lutg = p.luts + (size_t)f * 4096;
     const unsigned long long g = sp.g0 + (unsigned long long)blockIdx.x * kDecThreads + tid;
     if (g > sp.g1) return;
     const SubInfo in = p.subs[(size_t)f * p.subs_per_file + (g - sp.g0)];
@@ -776,8 +887,8 @@ __global__ void __launch_bounds__(kDecThreads) decode_write_kernel(DecodeParams 
     const unsigned long long hi_abs = (g + 1) * kSubBits;
     if (in.start < hi_abs) {
         uint8_t* dl = p.delta + (size_t)f * pitch * h;
-        if (chans == 4) decode_write_range<4>(sm, s_lut, in.start, (uint32_t)(hi_abs - in.start), dl, pitch, bpl, h, in.exit /*out_pos*/, in.lits /*tail*/, &err);
-        else decode_write_range<3>(sm, s_lut, in.start, (uint32_t)(hi_abs - in.start), dl, pitch, bpl, h, in.exit /*out_pos*/, in.lits /*tail*/, &err);
+        if (chans == 4) decode_write_range<4>(sm, s_fast, lutg, in.start, (uint32_t)(hi_abs - in.start), dl, pitch, bpl, h, in.exit /*out_pos*/, in.lits /*tail*/, &err);
+        else decode_write_range<3>(sm, s_fast, lutg, in.start, (uint32_t)(hi_abs - in.start), dl, pitch, bpl, h, in.exit /*out_pos*/, in.lits /*tail*/, &err);
     }
     if (err) stp->status = 1;
 }
@@ -933,7 +1044,7 @@ void launch_decode(const DecodeParams& p, uint32_t n, uint32_t desired, cudaStre
     DEC_MARK(1);
     const uint32_t sub_blocks = (p.subs_per_file + kDecThreads - 1) / kDecThreads;
     dim3 gsub(sub_blocks, n);
-    constexpr size_t kDecSmem = (4096 + kWinSmemWords) * 4;
+    constexpr size_t kDecSmem = (kFastWords + kWinSmemWords) * 4;
     FPNGB_SET_SMEM(decode_scan_kernel, kDecSmem);
     FPNGB_SET_SMEM(decode_write_kernel, kDecSmem);
     decode_scan_kernel<<<gsub, kDecThreads, kDecSmem, s>>>(p);

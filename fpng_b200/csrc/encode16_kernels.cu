@@ -344,6 +344,14 @@ __device__ __forceinline__ void put_event16(BitStager16& bs, uint32_t s_match_sa
     if (len) put_match16(bs, s_match_saddr, len);
 }
 
+// one Horner step of the in-kernel CRC: the register (XOR-ed with the lane's previous word) advanced over 128 bytes, then the next
+// word (slice tables [4][256] at shared address crc_s; byte extraction with PRMT so that each look-up address is one LEA)
+__device__ __forceinline__ uint32_t crc_step16(uint32_t crc_s, uint32_t cx, uint32_t v)
+{
+    const uint32_t b0 = cx & 0xFFu, b1 = __byte_perm(cx, 0u, 0x4441), b2 = __byte_perm(cx, 0u, 0x4442), b3 = cx >> 24;
+    return v ^ lds_u32(crc_s + b0 * 4u) ^ lds_u32(crc_s + 1024u + b1 * 4u) ^ lds_u32(crc_s + 2048u + b2 * 4u) ^ lds_u32(crc_s + 3072u + b3 * 4u);
+}
+
 template <int CHANS, bool DIRECT>
 __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParams p, uint32_t rows_per_warp)
 {
@@ -544,13 +552,21 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         // ---- flush the complete words; carry the partial one in a register
         leftover = stage[nwords];
         // lanes take the words in scanline order rotated by the words already flushed, so that a lane always sees stride 32
-        for (uint32_t j = (lane - (flushed_bits >> 5)) & 31u; j < nwords; j += 32) {
-            const uint32_t v = stage[j];
-            if (first_pending && j == 0) atomicOr(gptr, v);
-            else gptr[j] = v;
-            if (do_crc)
-                cx = v ^ lds_u32(crc_s + ((cx & 0xFFu) << 2)) ^ lds_u32(crc_s + 1024u + ((cx >> 6) & 0x3FCu)) ^
-                     lds_u32(crc_s + 2048u + ((cx >> 14) & 0x3FCu)) ^ lds_u32(crc_s + 3072u + ((cx >> 22) & 0x3FCu));
+        {
+            uint32_t j = (lane - (flushed_bits >> 5)) & 31u;
+            const uint32_t* sp = stage + j;
+            uint32_t* gp = gptr + j;
+            if (first_pending && j == 0u && nwords) {                    // the scanline's first word is shared with its predecessor
+                const uint32_t v = *sp;
+                atomicOr(gp, v);
+                if (do_crc) cx = crc_step16(crc_s, cx, v);
+                j = 32u; sp += 32; gp += 32;
+            }
+            for (; j < nwords; j += 32u, sp += 32, gp += 32) {
+                const uint32_t v = *sp;
+                *gp = v;
+                if (do_crc) cx = crc_step16(crc_s, cx, v);
+            }
         }
         __syncwarp();                                                    // staging is rewritten by the next step
         if (nwords) first_pending = false;
@@ -562,9 +578,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
             if (do_crc) {
                 // the partial word (possibly empty) counts as word Wn; every lane's value is shifted to the end of word Wn
                 const uint32_t Wn = flushed_bits >> 5;
-                if (lane == (Wn & 31u))
-                    cx = leftover ^ lds_u32(crc_s + ((cx & 0xFFu) << 2)) ^ lds_u32(crc_s + 1024u + ((cx >> 6) & 0x3FCu)) ^
-                         lds_u32(crc_s + 2048u + ((cx >> 14) & 0x3FCu)) ^ lds_u32(crc_s + 3072u + ((cx >> 22) & 0x3FCu));
+                if (lane == (Wn & 31u)) cx = crc_step16(crc_s, cx, leftover);
                 const uint32_t* lm = p.crc_lane_mul + (31u - ((Wn - lane) & 31u)) * 128u;    // x^(32 * (words after the lane's last + 1))
                 uint32_t r = __ldg(lm + (cx & 15u));
 #pragma unroll
