@@ -452,8 +452,12 @@ def run_ours(args, wl):
         L.fpngb_decode_profile_enable.argtypes = [C.c_int]
         L.fpngb_decode_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int]
         L.fpngb_decode_profile_enable(1)
+        L.fpngb_debug_decode_repairs.restype = C.c_ulonglong
+        L.fpngb_debug_decode_repairs.argtypes = [C.c_int]
+        L.fpngb_debug_decode_repairs(1)
         dstep()
         torch.cuda.synchronize(dev)
+        repairs = int(L.fpngb_debug_decode_repairs(1))
         dprof = (C.c_float * 6)()
         have_dprof = L.fpngb_decode_profile_read(dprof, 6)
         L.fpngb_decode_profile_enable(0)
@@ -461,6 +465,7 @@ def run_ours(args, wl):
                           "pixels_match_input": dec_ok, "algorithmic_gbs": dec_bytes / 1e9 / (dms / 1e3),
                           "frac_of_peak": dec_bytes / 1e9 / (dms / 1e3) / peak,
                           "input": dec_input,
+                          "link_repairs_per_call": repairs,     # subsequences whose speculative start was wrong (decoded again by the link pass)
                           "kernels_ms": dict(zip(["prepare", "scan", "link", "write", "stored", "unfilter"], [float(v) for v in dprof])) if have_dprof else None}
         # end to end through the C ABI with host buffers: files (pinned) -> H2D -> kernels -> D2H pixels (pinned)
         hfiles = torch.zeros((n, fstride), dtype=torch.uint8).pin_memory()

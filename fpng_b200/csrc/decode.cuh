@@ -47,5 +47,6 @@ struct DecodeParams {
 void launch_decode(const DecodeParams& p, uint32_t n, uint32_t desired, cudaStream_t s);
 void decode_profile_enable(bool on);
 int decode_profile_read(float* ms, int n);
+unsigned long long decode_link_repairs(bool reset);
 
 }  // namespace fpngb

@@ -487,14 +487,14 @@ __device__ __forceinline__ uint32_t win_peek(const uint32_t* __restrict__ win, u
 // literals could start at or beyond `limit` (the subsequence boundary) is cut down to its first literal.  Returns false when
 // the entry is not fast (L = 0); then `w` still holds the 32 stream bits for the fall-back.
 struct FastTok { uint32_t L, cnt, payload, w; };
-__device__ __forceinline__ bool fast_tok(const uint32_t* __restrict__ win, const uint32_t* __restrict__ s_fast, uint32_t q, uint32_t rel, uint32_t limit, FastTok& t)
+__device__ __forceinline__ bool fast_tok(const uint32_t* __restrict__ win, const uint32_t* __restrict__ s_fast, uint32_t sizes_s, uint32_t q, uint32_t rel, uint32_t limit, FastTok& t)
 {
     t.w = win_peek(win, q);
     const uint32_t e = s_fast[t.w & 4095u];
     t.L = e & 15u; t.cnt = (e >> 4) & 3u; t.payload = e >> 8;
     if (t.cnt >= 2u && rel + 12u > limit) {
         t.payload &= 0xFFu; t.cnt = 1u;
-        t.L = reinterpret_cast<const uint8_t*>(s_fast + 4096)[t.payload];
+        asm("ld.shared.u8 %0, [%1];\n" : "=r"(t.L) : "r"(sizes_s + t.payload));      // code size of the first literal
     }
     return t.L != 0u;
 }
@@ -519,8 +519,9 @@ __device__ __forceinline__ SubScan scan_window(const uint32_t* __restrict__ win,
 {
     SubScan r; r.first = lo; r.exit = 0; r.eob_end = 0; r.n_out = 0; r.nlit = 0; r.lits = 0;
     FastTok t;
+    const uint32_t sizes_s = (uint32_t)__cvta_generic_to_shared(s_fast + 4096);
     while (rel < lo) {                                                       // pre-roll: lock on to the token grid
-        if (fast_tok(win, s_fast, O + rel, rel, lo, t)) { rel += t.L; continue; }
+        if (fast_tok(win, s_fast, sizes_s, O + rel, rel, lo, t)) { rel += t.L; continue; }
         uint32_t sym, run;
         const uint32_t l = slow_tok(lutg, t.w, sym, run);
         if (!l || sym == 256u) { rel = lo; break; }                          // not locked on
@@ -529,7 +530,7 @@ __device__ __forceinline__ SubScan scan_window(const uint32_t* __restrict__ win,
     r.first = rel;
     uint32_t lits = 0, n_out = 0, nlit = 0;
     while (rel < hi) {
-        if (fast_tok(win, s_fast, O + rel, rel, hi, t)) {
+        if (fast_tok(win, s_fast, sizes_s, O + rel, rel, hi, t)) {
             rel += t.L;
             n_out += t.cnt ? t.cnt : t.payload;
             nlit += t.cnt;
@@ -595,16 +596,22 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
         else { if (row >= h) { *err = 1; return; } FPNGB_EMIT(s__); } \
     } while (0)
 
+    // literal fast path allowed: inside a scanline (filter byte consumed, row valid) with the pending bytes word aligned; the fast path
+    // itself keeps this true, every other path re-evaluates it when it is done
+    bool fastok;
+#define FPNGB_REFLAG() (fastok = !need_filter && row < h && (nacc | ((dcol & 3u) == 0u)))
+    FPNGB_REFLAG();
     FastTok t;
+    const uint32_t sizes_s = (uint32_t)__cvta_generic_to_shared(s_fast + 4096);
     while (rel < hi) {
         uint32_t run;
-        if (fast_tok(win, s_fast, O + rel, rel, hi, t)) {
+        if (fast_tok(win, s_fast, sizes_s, O + rel, rel, hi, t)) {
             rel += t.L;
             if (t.cnt) {
                 const uint32_t cnt = t.cnt, P = t.payload;
                 // fast path (almost every literal): inside a scanline, the pending bytes word aligned -- append the one to three bytes
                 // to the 64-bit accumulator, store a word when four are there; no per-byte branches
-                if (!need_filter && (nacc | ((dcol & 3u) == 0u)) && dcol + cnt < bpl && row < h) {
+                if (fastok && dcol + cnt < bpl) {
                     lits = __funnelshift_r(lits, P, 8u * cnt);
                     acc |= (unsigned long long)P << (8u * nacc);
                     nacc += cnt; dcol += cnt;
@@ -624,6 +631,7 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
                 FPNGB_LITERAL(P & 0xFFu);
                 if (cnt > 1u) FPNGB_LITERAL((P >> 8) & 0xFFu);
                 if (cnt > 2u) FPNGB_LITERAL(P >> 16);
+                FPNGB_REFLAG();
                 continue;
             }
             run = t.payload;
@@ -633,7 +641,7 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
             if (!l) return;                                                // invalid code: the link pass already flagged it
             if (sym == 256u) break;
             rel += l;
-            if (sym < 256u) { FPNGB_FLUSHQ(); FPNGB_LITERAL(sym); continue; }
+            if (sym < 256u) { FPNGB_FLUSHQ(); FPNGB_LITERAL(sym); FPNGB_REFLAG(); continue; }
         }
         {
             FPNGB_FLUSHQ();
@@ -678,11 +686,13 @@ __device__ __forceinline__ void decode_write_range(const Stream& st, const uint3
                 }
                 while (left) { FPNGB_EMIT((px >> (8u * ph)) & 0xFFu); ph = ph == 2u ? 0u : ph + 1u; left--; }
             }
+            FPNGB_REFLAG();
         }
     }
     FPNGB_FLUSHQ();
     for (uint32_t i = 0; i < nacc; i++) rowp[dcol - nacc + i] = (uint8_t)(acc >> (8u * i));
 #undef FPNGB_FLUSHQ
+#undef FPNGB_REFLAG
 #undef FPNGB_EMIT
 #undef FPNGB_LITERAL
 }
@@ -744,12 +754,24 @@ __global__ void __launch_bounds__(kDecThreads) decode_scan_kernel(DecodeParams p
     info->n_out = r.n_out; info->lits = r.lits; info->nlit = min(r.nlit, 4u);
 }
 
+// statistics: subsequences whose speculative start was wrong and had to be decoded again by the link pass (fpngb_debug_decode_repairs)
+__device__ unsigned long long g_link_repairs = 0ull;
+unsigned long long decode_link_repairs(bool reset)
+{
+    unsigned long long v = 0, z = 0;
+    cudaMemcpyFromSymbol(&v, g_link_repairs, sizeof v);
+    if (reset) cudaMemcpyToSymbol(g_link_repairs, &z, sizeof z);
+    return v;
+}
+
 __global__ void __launch_bounds__(kLinkThreads) decode_link_kernel(DecodeParams p)
 {
     __shared__ uint32_t s_lut[4096];
     __shared__ unsigned long long s_exit[kLinkThreads];
     __shared__ unsigned long long s_scan[kLinkThreads / 32];
     __shared__ uint32_t s_litn[kLinkThreads / 32], s_litv[kLinkThreads / 32];
+    __shared__ unsigned long long s_wbase[kLinkThreads / 32], s_chunk_total;
+    __shared__ uint32_t s_wlitn[kLinkThreads / 32], s_wlitv[kLinkThreads / 32], s_chunk_litn, s_chunk_litv;
     __shared__ unsigned long long s_carry_start, s_carry_out, s_eob_end;
     __shared__ uint32_t s_carry_litn, s_carry_litv, s_done, s_err, s_first_bad, s_lut_loaded;
 
@@ -768,12 +790,15 @@ __global__ void __launch_bounds__(kLinkThreads) decode_link_kernel(DecodeParams 
     if (tid == 0) { s_carry_start = sp.tok0; s_carry_out = 0; s_carry_litn = 0; s_carry_litv = 0; s_done = 0; s_err = 0; s_eob_end = 0; s_lut_loaded = 0; }
     __syncthreads();
 
+    SubInfo nxt;                                       // the next chunk's records are loaded while this chunk is processed
+    if (tid < nsub) nxt = subs[tid];
     for (unsigned long long base = 0; base < nsub; base += kLinkThreads) {
         const unsigned long long i = base + tid;
         const bool have = i < nsub;
         SubInfo in;
-        if (have) in = subs[i];
+        if (have) in = nxt;
         else { in.start = 0; in.exit = kPosErr; in.eob_end = 0; in.n_out = 0; in.lits = 0; in.nlit = 0; }
+        if (i + kLinkThreads < nsub) nxt = subs[i + kLinkThreads];
         const unsigned long long g = sp.g0 + i;
         // ---- verify / repair the chain: every subsequence must start where its predecessor exits
         for (uint32_t iter = 0;; iter++) {
@@ -788,6 +813,7 @@ __global__ void __launch_bounds__(kLinkThreads) decode_link_kernel(DecodeParams 
                 if (tid == 0) s_lut_loaded = 1;
             }
             if (mismatch) {
+                atomicAdd(&g_link_repairs, 1ull);
                 const unsigned long long hi_abs = (g + 1) * kSubBits;
                 if (want >= hi_abs) { in.start = want; in.exit = want; in.n_out = 0; in.nlit = 0; in.lits = 0; }   // cannot happen for kSubBits >> token size
                 else {
@@ -822,13 +848,35 @@ __global__ void __launch_bounds__(kLinkThreads) decode_link_kernel(DecodeParams 
         uint32_t en = __shfl_up_sync(kFullMask, wn, 1), ev = __shfl_up_sync(kFullMask, wv, 1);
         if (lane == 0) { ex = 0; en = 0; ev = 0; }
         __syncthreads();
-        unsigned long long wbase = 0, chunk_total = 0;
-        uint32_t bn = s_carry_litn, bv = s_carry_litv, cn = bn, cv = bv;
-        for (uint32_t k = 0; k < kLinkThreads / 32; k++) {
-            if (k < warp) { wbase += s_scan[k]; lit_combine(bn, bv, s_litn[k], s_litv[k]); }
-            chunk_total += s_scan[k];
-            lit_combine(cn, cv, s_litn[k], s_litv[k]);
+        // second level: warp 0 scans the (<= 32) warp totals, carry of the earlier chunks folded in
+        static_assert(kLinkThreads / 32 <= 32, "one warp scans the warp totals");
+        if (warp == 0) {
+            const bool hw = lane < kLinkThreads / 32;
+            unsigned long long t = hw ? s_scan[lane] : 0ull;
+            uint32_t tn = hw ? s_litn[lane] : 0u, tv = hw ? s_litv[lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(kFullMask, t, o);
+                const uint32_t un = __shfl_up_sync(kFullMask, tn, o), uv = __shfl_up_sync(kFullMask, tv, o);
+                if (lane >= (uint32_t)o) { t += up; uint32_t an = un, av = uv; lit_combine(an, av, tn, tv); tn = an; tv = av; }
+            }
+            // exclusive form, then the carry in front
+            unsigned long long xt = __shfl_up_sync(kFullMask, t, 1);
+            uint32_t xn = __shfl_up_sync(kFullMask, tn, 1), xv = __shfl_up_sync(kFullMask, tv, 1);
+            if (lane == 0) { xt = 0; xn = 0; xv = 0; }
+            uint32_t bn0 = s_carry_litn, bv0 = s_carry_litv;
+            lit_combine(bn0, bv0, xn, xv);
+            if (hw) { s_wbase[lane] = xt; s_wlitn[lane] = bn0; s_wlitv[lane] = bv0; }
+            if (lane == 31) {                                             // lanes beyond the last warp carry zeros: lane 31 holds the chunk totals
+                uint32_t cn0 = s_carry_litn, cv0 = s_carry_litv;
+                lit_combine(cn0, cv0, tn, tv);
+                s_chunk_total = t; s_chunk_litn = cn0; s_chunk_litv = cv0;
+            }
         }
+        __syncthreads();
+        const unsigned long long wbase = s_wbase[warp], chunk_total = s_chunk_total;
+        uint32_t bn = s_wlitn[warp], bv = s_wlitv[warp];
+        const uint32_t cn = s_chunk_litn, cv = s_chunk_litv;
         lit_combine(bn, bv, en, ev);
         const unsigned long long out_pos = s_carry_out + wbase + ex;
 

@@ -239,6 +239,38 @@ __device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volati
 __device__ __forceinline__ void reds_or_u32(uint32_t saddr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;\n" :: "r"(saddr), "r"(v)); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr)); return v; }
 
+// FPNGB_PACK_MUL (A/B build, default off): the stager shifts by MULTIPLYING.  The pack kernel is bound by the ALU pipe (LOP3 / SHF /
+// IADD3 / ISETP: ncu 76 % active, math-pipe-throttle the top stall) while the FMA pipe is mostly idle, so with the fill level kept as
+// m = 2^n, "cur | code << n" becomes code * m + cur (IMAD; the operands never overlap, so + is |), the spill IMAD.HI, the new level
+// m * 2^len (its high word is non-zero exactly when the word is complete) and a pair of codes c0 + c1 * 2^l0; the tables then hold
+// 2^size instead of size.  Byte-exact, but MEASURED SLOWER on B200 (C2 pack 1.445 vs 1.396 ms, ODD 1.934 vs 1.769): the wide / high
+// multiplies make the FMA pipe the new limiter.  Kept for the record (profiles/README.md).
+#ifndef FPNGB_PACK_MUL
+#define FPNGB_PACK_MUL 0
+#endif
+#if FPNGB_PACK_MUL
+struct BitStager16 {
+    uint32_t cur;               // the word being filled
+    uint32_t m;                 // 2^n, n = valid bits in it (n < 32)
+    uint32_t dst;               // shared-memory address of the staging word it goes to
+    __device__ __forceinline__ void begin(uint32_t stage_saddr, uint32_t bitpos, uint32_t seed)
+    {
+        cur = seed; m = 1u << (bitpos & 31u); dst = stage_saddr + ((bitpos >> 5) << 2);
+    }
+    // append a code of `len` bits given as pw = 2^len (len <= 24, code < pw); pw == 1 (code == 0) is a no-op
+    __device__ __forceinline__ void put_pow(uint32_t code, uint32_t pw)
+    {
+        const uint32_t lo = code * m + cur;                             // cur < m and code * m is a multiple of m: + is |
+        const uint32_t hi = __umulhi(code, m);                          // bits that spill into the next word
+        const uint32_t mlo = m * pw, mhi = __umulhi(m, pw);             // 2^(n + len): the high word is set iff the word is complete
+        if (mhi) { sts_u32(dst, lo); dst += 4u; cur = hi; m = mhi; }    // this lane owns bit 31 of the word: plain store
+        else { cur = lo; m = mlo; }
+    }
+    __device__ __forceinline__ void put(uint32_t code, uint32_t len) { put_pow(code, 1u << len); }
+    // after a warp barrier: the partial last word is shared with the next lane's first word
+    __device__ __forceinline__ void end() { if (cur) reds_or_u32(dst, cur); }
+};
+#else
 struct BitStager16 {
     uint32_t cur, n;            // word being filled (n < 32 valid bits)
     uint32_t dst;               // shared-memory address of the staging word `cur` goes to
@@ -258,6 +290,7 @@ struct BitStager16 {
     // after a warp barrier: the partial last word is shared with the next lane's first word
     __device__ __forceinline__ void end() { if (cur) reds_or_u32(dst, cur); }
 };
+#endif
 
 __device__ __forceinline__ void put_pair16(BitStager16& bs, uint32_t a, uint32_t b)   // two table entries (len << 16 | code), <= 24 bits
 {
@@ -310,8 +343,13 @@ __device__ __forceinline__ void put_word16(BitStager16& bs, uint32_t s_lit_saddr
     const uint32_t l64 = s_lit_saddr - 4096u, nb8 = nb << 1;
     const uint2 f0 = lds_u64(l64 + lit_off16x8<0>(w, nb8)), f1 = lds_u64(l64 + lit_off16x8<1>(w, nb8));
     const uint2 f2 = lds_u64(l64 + lit_off16x8<2>(w, nb8)), f3 = lds_u64(l64 + lit_off16x8<3>(w, nb8));
+#if FPNGB_PACK_MUL
+    bs.put_pow(f0.x + f1.x * f0.y, f0.y * f1.y);                         // the table holds (code, 2^size)
+    bs.put_pow(f2.x + f3.x * f2.y, f2.y * f3.y);
+#else
     bs.put(f0.x | (f1.x << f0.y), f0.y + f1.y);
     bs.put(f2.x | (f3.x << f2.y), f2.y + f3.y);
+#endif
     return;
 #endif
     const uint32_t e0 = lds_u32(s_lit_saddr + lit_off16<0>(w, nb)), e1 = lds_u32(s_lit_saddr + lit_off16<1>(w, nb));
@@ -387,7 +425,11 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
         const uint32_t e = book->lit[i];
         s_lit[i] = e; s_lit[256 + i] = 0u;
 #if FPNGB_PACK_LIT64
+#if FPNGB_PACK_MUL
+        s_lit64[2 * i] = e & 0xFFFFu; s_lit64[2 * i + 1] = 1u << (e >> 16); s_lit64[512 + 2 * i] = 0u; s_lit64[512 + 2 * i + 1] = 1u;   // (code, 2^size); null: 2^0
+#else
         s_lit64[2 * i] = e & 0xFFFFu; s_lit64[2 * i + 1] = e >> 16; s_lit64[512 + 2 * i] = 0u; s_lit64[512 + 2 * i + 1] = 0u;
+#endif
 #endif
     }
     if (threadIdx.x < 88) s_match[threadIdx.x] = book->match[threadIdx.x];
