@@ -1000,7 +1000,10 @@ __global__ void __launch_bounds__(128) unfilter_kernel(DecodeParams p)
     const uint32_t w = p.w, h = p.h, pitch = p.delta_pitch;
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;                   // pixel group index
     const uint32_t x0 = g * 4;
+    const uint32_t amask = __ballot_sync(kFullMask, x0 < w);                     // lanes of this warp that own a group (they stay converged)
     if (x0 >= w) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool next_full = lane < 31u && x0 + 8u <= w;                           // the next lane of this warp owns a whole group
     const uint32_t npx = min(4u, w - x0);
     const uint8_t* delta = p.delta + (size_t)f * pitch * h + (size_t)x0 * SRC;
     uint8_t* out = p.d_out + (size_t)f * p.out_stride + (size_t)x0 * DST;
@@ -1048,9 +1051,23 @@ __global__ void __launch_bounds__(128) unfilter_kernel(DecodeParams p)
                 o[DST - 1] = __byte_perm(acc[2], acc[SRC - 1], 0x6542);
             }
             uint8_t* orow = out + (size_t)y * out_pitch;
-            if (full && out_aligned) {
+            // output scanlines of any width (w * DST need not be a multiple of 4: 687 x 3 = 2061): the misalignment is the same for every
+            // group of a scanline (groups are 4 * DST bytes apart), so the aligned words a thread's bytes straddle are assembled with
+            // one funnel shift each, the word shared with the previous group from that lane's last word (shuffle); only the two ends
+            // of a warp's stretch go out as single bytes
+            const uint32_t prev_last = __shfl_up_sync(amask, o[DST - 1], 1);
+            const uint32_t mis = (uint32_t)((uintptr_t)orow & 3u);
+            if (full && (out_aligned || mis == 0u)) {
 #pragma unroll
                 for (int i = 0; i < DST; i++) *reinterpret_cast<uint32_t*>(orow + 4 * i) = o[i];
+            } else if (full) {
+                const uint32_t sh = 8u * (4u - mis);
+                uint8_t* ab = orow - mis;                                        // 4-byte aligned
+                if (lane > 0u) *reinterpret_cast<uint32_t*>(ab) = __funnelshift_r(prev_last, o[0], sh);
+                else for (uint32_t b = 0; b < 4u - mis; b++) orow[b] = (uint8_t)(o[0] >> (8u * b));
+#pragma unroll
+                for (int i = 1; i < DST; i++) *reinterpret_cast<uint32_t*>(ab + 4 * i) = __funnelshift_r(o[i - 1], o[i], sh);
+                if (!next_full) for (uint32_t b = 0; b < mis; b++) orow[4u * DST - mis + b] = (uint8_t)(o[DST - 1] >> (8u * (4u - mis + b)));
             } else {
 #pragma unroll
                 for (int i = 0; i < DST; i++) for (int b = 0; b < 4; b++) if ((uint32_t)(4 * i + b) < npx * DST) orow[4 * i + b] = (uint8_t)(o[i] >> (8 * b));

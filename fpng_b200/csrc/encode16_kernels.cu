@@ -52,11 +52,14 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
     uint8_t* s_lit = dyn_smem + kScan16Rows * WK::kWarpBytes;
     uint8_t* s_match = s_lit + 256;
 
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the warp index as a shuffle result: the compiler then treats everything derived from it (scanline pointers, tile address) as
+    // warp-uniform and issues the TMA copies from uniform registers without a per-lane "waterfall" loop
+    const uint32_t lane = threadIdx.x & 31, warp = __shfl_sync(kFullMask, threadIdx.x >> 5, 0);
     const uint32_t img = blockIdx.y;
     const uint32_t y = blockIdx.x * kScan16Rows + warp;
     const CodeBook* book = p.books + (size_t)img * p.book_stride;
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = book->lit_size[i];
+    static_assert(32 * kScan16Rows == 256, "one table byte per thread");
+    s_lit[threadIdx.x] = book->lit_size[threadIdx.x];
     if (threadIdx.x < 88) s_match[threadIdx.x] = book->match_bits[threadIdx.x];
     __syncthreads();
     if (y >= p.h) return;
@@ -92,10 +95,16 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams
 #pragma unroll
                 for (int k = 0; k < 16; k++) bits += literal_bits16<CHANS>(s_lit, px[k]);
             } else {
+                // mixed step: the per-pixel sizes (<= 48) of four pixels packed into one word (IMADs) and added under the literal mask
+                // by ONE dp4a against the nibble spread to 0/1 bytes -- instead of three ALU-pipe mask instructions per pixel
+                const uint32_t k8 = c_fma_k[2], k16 = c_fma_k[3], k24 = c_fma_k[4];
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const uint32_t c = literal_bits16<CHANS>(s_lit, px[k]);
-                    bits += (t.litm & (1u << k)) ? c : 0u;
+                for (int g = 0; g < 4; g++) {
+                    const uint32_t c0 = literal_bits16<CHANS>(s_lit, px[4 * g]), c1 = literal_bits16<CHANS>(s_lit, px[4 * g + 1]);
+                    const uint32_t c2 = literal_bits16<CHANS>(s_lit, px[4 * g + 2]), c3 = literal_bits16<CHANS>(s_lit, px[4 * g + 3]);
+                    const uint32_t packed = c3 * k24 + (c2 * k16 + (c1 * k8 + c0));
+                    const uint32_t m01 = (((t.litm >> (4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;   // bit j of the nibble -> byte j
+                    bits = __dp4a(packed, m01, bits);
                 }
             }
         }
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(32 * kScan16Rows) row_hist16_kernel(ScanParams
     uint32_t* s_hist_all = reinterpret_cast<uint32_t*>(dyn_smem + kScan16Rows * WK::kWarpBytes);   // [warps][288]
     __shared__ uint16_t s_lensym[88];
 
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31, warp = __shfl_sync(kFullMask, threadIdx.x >> 5, 0);   // warp-uniform for the compiler (see the scan kernel)
     const uint32_t img = blockIdx.y;
     const uint32_t y = blockIdx.x * kScan16Rows + warp;
     for (uint32_t i = threadIdx.x; i < kScan16Rows * 288; i += blockDim.x) s_hist_all[i] = 0u;
@@ -408,7 +417,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
     uint32_t* s_stage_all = s_match + 88;
     uint32_t* s_crc = s_stage_all + kPack16Rows * stage16_words<CHANS>();              // [4][256] CRC slice tables (row_crc only)
 
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31, warp = __shfl_sync(kFullMask, threadIdx.x >> 5, 0);   // warp-uniform for the compiler (see the scan kernel)
     const uint32_t img = blockIdx.y;
     const uint32_t row0 = (blockIdx.x * kPack16Rows + warp) * rows_per_warp;           // this warp's first scanline
     const bool do_crc = p.row_crc != nullptr;

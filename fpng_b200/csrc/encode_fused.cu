@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, CHANS == 3 ? 4 : 3) encode_f
     // s_small: [0..7] has_lit, [8..15] trail, [16..23] npix, [24..31] unit bits, [32] ticket, [33] pred tail, [34] sh, [35] status
     unsigned long long* s_u64 = reinterpret_cast<unsigned long long*>(s_small + 48);     // [0..7] adler A, [8..15] adler B, [16] base (file bit of the group's first bit)
 
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = __shfl_sync(kFullMask, threadIdx.x >> 5, 0), tid = threadIdx.x;
     // Row groups are processed in stream order.  CTAs of a 1-D grid are dispatched in blockIdx order on every NVIDIA GPU (the
     // decoupled look-back of CUB's device-wide scan relies on the same property), so a group only waits for groups that are
     // already resident; FPNGB_FUSED_TICKET=1 (build flag) switches to an atomic ticket, which does not depend on that.

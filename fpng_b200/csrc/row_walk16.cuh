@@ -54,6 +54,42 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                  :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
+
+// The encode kernels are bound by the ALU pipe (LOP3 / SHF / IADD3 / ISETP / SEL; ncu: ~77 % active) while the FMA pipe idles (~17 %).
+// Multipliers the compiler cannot fold keep a few add / shift-add steps on the FMA pipe as IMAD with a constant-bank operand
+// (a literal 2 or -1 would be strength-reduced to LEA / IADD3, ALU-pipe instructions): {2, -1, 2^8, 2^16, 2^24}.
+static __constant__ uint32_t c_fma_k[5] = {2u, 0xFFFFFFFFu, 1u << 8, 1u << 16, 1u << 24};
+
+// Adler-32 partial sums of one 16-byte chunk at byte offset 16 * I of the lane's bytes: t1 += sum of bytes, t2 += sum of (position inside
+// the lane's bytes) * byte.  The position weights fold the chunk offset (<= 63: a u8), so a step needs ONE 64-bit multiply-add per lane
+// (lane_base * T1 + T2) instead of one per chunk.
+template <int I>
+__device__ __forceinline__ void adler_chunk16(const uint4& d, uint32_t& t1, uint32_t& t2)
+{
+    constexpr uint32_t kW = 0x03020100u + 0x01010101u * (16u * I);
+    t1 = __dp4a(d.x, 0x01010101u, t1); t2 = __dp4a(d.x, kW, t2);
+    t1 = __dp4a(d.y, 0x01010101u, t1); t2 = __dp4a(d.y, kW + 0x04040404u, t2);
+    t1 = __dp4a(d.z, 0x01010101u, t1); t2 = __dp4a(d.z, kW + 0x08080808u, t2);
+    t1 = __dp4a(d.w, 0x01010101u, t1); t2 = __dp4a(d.w, kW + 0x0C0C0C0Cu, t2);
+}
+template <int I, int N> struct AdlerChunks {
+    __device__ __forceinline__ static void run(const uint32_t* dw, uint32_t& t1, uint32_t& t2)
+    {
+        adler_chunk16<I>(make_uint4(dw[4 * I], dw[4 * I + 1], dw[4 * I + 2], dw[4 * I + 3]), t1, t2);
+        AdlerChunks<I + 1, N>::run(dw, t1, t2);
+    }
+};
+template <int N> struct AdlerChunks<N, N> { __device__ __forceinline__ static void run(const uint32_t*, uint32_t&, uint32_t&) {} };
+// all CHANS chunks of a lane's filtered words; sumA / sumB are the scanline's running sums (bytes, position-weighted bytes)
+template <int CHANS>
+__device__ __forceinline__ void adler_lane16(const uint32_t (&dw)[4 * CHANS], uint32_t lane_base, uint32_t& sumA, unsigned long long& sumB)
+{
+    uint32_t t1 = 0, t2 = 0;
+    AdlerChunks<0, CHANS>::run(dw, t1, t2);
+    sumA += t1;
+    sumB += (unsigned long long)lane_base * t1 + t2;
+}
+
 template <int CHANS>
 struct Walk16Tma {
     static constexpr int kWords = 4 * CHANS;     // filtered words per lane per step (16 pixels)
@@ -96,26 +132,31 @@ struct Walk16Tma {
         const uint8_t* tc = warp_tiles + lane * (16 * CHANS);
         const uint8_t* tp = tc + kTile;
         const uint32_t lane_base = step * kStepBytes + lane * (16u * CHANS);     // byte offset of the lane's first byte in the row
+        if ((step + 1u) * kStepBytes <= bpl) {                                   // warp-uniform: the whole step lies inside the scanline
 #pragma unroll
-        for (int i = 0; i < CHANS; i++) {
-            uint4 d = make_uint4(0, 0, 0, 0);
-            if (lane_base + 16u * i < bpl) {                                     // bytes beyond the scanline were not copied
-                d = *reinterpret_cast<const uint4*>(tc + i * 16);
+            for (int i = 0; i < CHANS; i++) {
+                uint4 d = *reinterpret_cast<const uint4*>(tc + i * 16);
                 if (have_prev) {
                     const uint4 q = *reinterpret_cast<const uint4*>(tp + i * 16);
                     d.x = vsub4(d.x, q.x); d.y = vsub4(d.y, q.y); d.z = vsub4(d.z, q.z); d.w = vsub4(d.w, q.w);
                 }
-                if (kAdler) {
-                    uint32_t t1 = __dp4a(d.x, 0x01010101u, 0u), t2 = __dp4a(d.x, 0x03020100u, 0u);
-                    t1 = __dp4a(d.y, 0x01010101u, t1); t2 = __dp4a(d.y, 0x07060504u, t2);
-                    t1 = __dp4a(d.z, 0x01010101u, t1); t2 = __dp4a(d.z, 0x0B0A0908u, t2);
-                    t1 = __dp4a(d.w, 0x01010101u, t1); t2 = __dp4a(d.w, 0x0F0E0D0Cu, t2);
-                    sumA += t1;
-                    sumB += (unsigned long long)(lane_base + 16u * i) * t1 + t2;
-                }
+                dw[4 * i] = d.x; dw[4 * i + 1] = d.y; dw[4 * i + 2] = d.z; dw[4 * i + 3] = d.w;
             }
-            dw[4 * i] = d.x; dw[4 * i + 1] = d.y; dw[4 * i + 2] = d.z; dw[4 * i + 3] = d.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < CHANS; i++) {
+                uint4 d = make_uint4(0, 0, 0, 0);
+                if (lane_base + 16u * i < bpl) {                                 // bytes beyond the scanline were not copied
+                    d = *reinterpret_cast<const uint4*>(tc + i * 16);
+                    if (have_prev) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(tp + i * 16);
+                        d.x = vsub4(d.x, q.x); d.y = vsub4(d.y, q.y); d.z = vsub4(d.z, q.z); d.w = vsub4(d.w, q.w);
+                    }
+                }
+                dw[4 * i] = d.x; dw[4 * i + 1] = d.y; dw[4 * i + 2] = d.z; dw[4 * i + 3] = d.w;
+            }
         }
+        if (kAdler) adler_lane16<CHANS>(dw, lane_base, sumA, sumB);
         __syncwarp();                                                            // every lane has its pixels: the tile may be refilled
     }
 
@@ -193,16 +234,9 @@ struct Walk16Padded {
                 const uint4 q = *reinterpret_cast<const uint4*>(tp + i * 16);
                 d.x = vsub4(d.x, q.x); d.y = vsub4(d.y, q.y); d.z = vsub4(d.z, q.z); d.w = vsub4(d.w, q.w);
             }
-            if (kAdler) {
-                uint32_t t1 = __dp4a(d.x, 0x01010101u, 0u), t2 = __dp4a(d.x, 0x03020100u, 0u);
-                t1 = __dp4a(d.y, 0x01010101u, t1); t2 = __dp4a(d.y, 0x07060504u, t2);
-                t1 = __dp4a(d.z, 0x01010101u, t1); t2 = __dp4a(d.z, 0x0B0A0908u, t2);
-                t1 = __dp4a(d.w, 0x01010101u, t1); t2 = __dp4a(d.w, 0x0F0E0D0Cu, t2);
-                sumA += t1;
-                sumB += (unsigned long long)(lane_base + 16u * i) * t1 + t2;
-            }
             dw[4 * i] = d.x; dw[4 * i + 1] = d.y; dw[4 * i + 2] = d.z; dw[4 * i + 3] = d.w;
         }
+        if (kAdler) adler_lane16<CHANS>(dw, lane_base, sumA, sumB);
         __syncwarp();
     }
     __device__ __forceinline__ static void pixels(const uint32_t (&dw)[kWords], uint32_t (&px)[16])
@@ -289,17 +323,7 @@ struct Walk16Direct {
 #pragma unroll
             for (int i = 0; i < kWords; i++) dw[i] = 0u;
         }
-        if (kAdler) {
-#pragma unroll
-            for (int i = 0; i < CHANS; i++) {
-                uint32_t t1 = __dp4a(dw[4 * i], 0x01010101u, 0u), t2 = __dp4a(dw[4 * i], 0x03020100u, 0u);
-                t1 = __dp4a(dw[4 * i + 1], 0x01010101u, t1); t2 = __dp4a(dw[4 * i + 1], 0x07060504u, t2);
-                t1 = __dp4a(dw[4 * i + 2], 0x01010101u, t1); t2 = __dp4a(dw[4 * i + 2], 0x0B0A0908u, t2);
-                t1 = __dp4a(dw[4 * i + 3], 0x01010101u, t1); t2 = __dp4a(dw[4 * i + 3], 0x0F0E0D0Cu, t2);
-                sumA += t1;
-                sumB += (unsigned long long)(lane_base + 16u * i) * t1 + t2;
-            }
-        }
+        if (kAdler) adler_lane16<CHANS>(dw, lane_base, sumA, sumB);
     }
     __device__ __forceinline__ static void pixels(const uint32_t (&dw)[kWords], uint32_t (&px)[16]) { Walk16Tma<CHANS>::pixels(dw, px); }
     __device__ __forceinline__ void bind(const uint8_t* cur, const uint8_t* prev) { cur_ = cur; prev_ = prev; }
@@ -322,6 +346,9 @@ struct Lane16 {
 // what the scan kernel hands to the pack kernel per lane and step: eqm | run << 16 | nvp << 23 | last << 28
 __device__ __forceinline__ uint32_t lane_info16(const Lane16& t) { return t.eqm | (t.run << 16) | (t.nvp << 23) | (t.last ? (1u << 28) : 0u); }
 
+// min(v, 1) as one VIMNMX (written in C++ the compiler turns it into compare + select: two ALU-pipe instructions)
+__device__ __forceinline__ uint32_t nonzero01(uint32_t v) { uint32_t r; asm("min.u32 %0, %1, 1;\n" : "=r"(r) : "r"(v)); return r; }
+
 template <int CHANS>
 __device__ __forceinline__ Lane16 classify16(const uint32_t (&px)[16], uint32_t p0, uint32_t w, RowCarry& carry, uint32_t lane)
 {
@@ -330,9 +357,14 @@ __device__ __forceinline__ Lane16 classify16(const uint32_t (&px)[16], uint32_t 
     t.nvp = p0 < w ? min(16u, w - p0) : 0u;
     uint32_t left = __shfl_up_sync(kFullMask, px[15], 1);
     if (lane == 0) left = carry.prev_px;
-    uint32_t eq = (p0 > 0 && px[0] == left) ? 1u : 0u;
+    // bit k of `ne`: pixel k differs from its left neighbour.  Per pixel one ALU-pipe instruction (min) and two IMADs (difference,
+    // shift-add into the mask) instead of compare + select + OR (see c_fma_k)
+    const uint32_t kTwo = c_fma_k[0], kM1 = c_fma_k[1];
+    uint32_t ne = 0;
 #pragma unroll
-    for (int k = 1; k < 16; k++) eq |= (px[k] == px[k - 1]) ? (1u << k) : 0u;
+    for (int k = 15; k >= 1; k--) ne = ne * kTwo + nonzero01(px[k - 1] * kM1 + px[k]);
+    ne = ne * kTwo + (p0 > 0 ? nonzero01(left * kM1 + px[0]) : 1u);
+    const uint32_t eq = ~ne;
     const uint32_t valid = (1u << t.nvp) - 1u;
     t.eqm = eq & valid;
     t.litm = valid & ~eq;
