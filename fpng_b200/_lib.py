@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
     L.fpngb_debug_crc_stream.argtypes = [C.c_int]
     L.fpngb_debug_inline_crc.restype = None
     L.fpngb_debug_inline_crc.argtypes = [C.c_int]
+    L.fpngb_debug_decode_staged.restype = None
+    L.fpngb_debug_decode_staged.argtypes = [C.c_int]
     L.fpngb_debug_rows_per_warp.restype = None
     L.fpngb_debug_rows_per_warp.argtypes = [C.c_uint32]
     L.fpngb_debug_static_table.restype = C.c_int

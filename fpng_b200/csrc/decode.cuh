@@ -48,5 +48,6 @@ void launch_decode(const DecodeParams& p, uint32_t n, uint32_t desired, cudaStre
 void decode_profile_enable(bool on);
 int decode_profile_read(float* ms, int n);
 unsigned long long decode_link_repairs(bool reset);
+void decode_set_staged(bool on);            // write pass through the shared-memory staged kernel (default) or decode_write_kernel alone
 
 }  // namespace fpngb

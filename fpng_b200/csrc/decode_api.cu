@@ -262,6 +262,7 @@ int fpngb_decode_batch_host(const void* const* files, const uint32_t* sizes, uin
 FPNGB_API int fpngb_decode_profile_enable(int on) { decode_profile_enable(on != 0); return 0; }
 FPNGB_API int fpngb_decode_profile_read(float* ms, int n) { return decode_profile_read(ms, n); }
 // test hook: number of subsequences the link pass had to decode again since the last reset (synchronises the device)
+FPNGB_API void fpngb_debug_decode_staged(int on) { decode_set_staged(on != 0); }   // tests / A/B: 0 = decode_write_kernel alone
 FPNGB_API unsigned long long fpngb_debug_decode_repairs(int reset) { cudaDeviceSynchronize(); return decode_link_repairs(reset != 0); }
 
 int fpngb_get_info_ex(const void* file, uint32_t size, uint32_t* w, uint32_t* h, uint32_t* chans, uint32_t* idat_ofs, uint32_t* idat_len)
