@@ -43,8 +43,15 @@ __device__ __forceinline__ uint32_t literal_bits16(const uint8_t* s_lit, uint32_
 // ------------------------------------------------------------------------------------------------
 // K1 (v2): per-row bit count + Adler partials (+ per-lane bit offsets inside the row for the pack kernel)
 // ------------------------------------------------------------------------------------------------
+// FPNGB_SCAN_MINB (A/B build): minimum CTAs per SM the scan kernel is compiled for (5 caps the RGB kernel at 48 registers: 40 instead of
+// 32 warps per SM).  Measured SLOWER on B200 (C2 scan 0.633 -> 0.658 ms, C3 1.380 -> 1.404): the kernel is ALU-pipe bound, not latency bound.
+#ifdef FPNGB_SCAN_MINB
+#define FPNGB_SCAN_BOUNDS __launch_bounds__(32 * kScan16Rows, FPNGB_SCAN_MINB)
+#else
+#define FPNGB_SCAN_BOUNDS __launch_bounds__(32 * kScan16Rows)
+#endif
 template <int CHANS, bool DIRECT>
-__global__ void __launch_bounds__(32 * kScan16Rows) row_scan16_kernel(ScanParams p)
+__global__ void FPNGB_SCAN_BOUNDS row_scan16_kernel(ScanParams p)
 {
     using WK = typename Loader16<CHANS, DIRECT>::type;
     constexpr uint32_t M = max_match_pixels(CHANS);
@@ -320,11 +327,27 @@ __device__ __forceinline__ void put_match16(BitStager16& bs, uint32_t s_match_sa
 #endif
 #if FPNGB_PACK_LIT64
 __device__ __forceinline__ uint2 lds_u64(uint32_t saddr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(saddr)); return v; }
+// FPNGB_PACK_OFS_FMA: the byte offset of a table entry as "extract the byte (one ALU-pipe instruction), multiply by 8 (IMAD with a
+// constant-bank operand, FMA pipe)" instead of shift + mask (two ALU-pipe instructions); only where no null-half bit is OR-ed in.
+// Measured on B200: pack 1.352 -> 1.341 ms (C2), 3.402 -> 3.370 ms (C3); =0 restores shift + mask.
+#ifndef FPNGB_PACK_OFS_FMA
+#define FPNGB_PACK_OFS_FMA 1
+#endif
 template <int POS>
 __device__ __forceinline__ uint32_t lit_off16x8(uint32_t w, uint32_t nb8)
 {
     const uint32_t x = POS == 0 ? (w << 3) : (POS == 1 ? (w >> 5) : (POS == 2 ? (w >> 13) : (w >> 21)));
     return (x & 0x7F8u) | nb8;
+}
+template <int POS>
+__device__ __forceinline__ uint32_t lit_off16x8_plain(uint32_t w)
+{
+#if FPNGB_PACK_OFS_FMA
+    const uint32_t b = POS == 0 ? (w & 0xFFu) : (POS == 1 ? byte1(w) : (POS == 2 ? byte2(w) : (w >> 24)));
+    return b * c_fma_k[5];
+#else
+    return lit_off16x8<POS>(w, 0u);
+#endif
 }
 #endif
 
@@ -345,13 +368,20 @@ __device__ __forceinline__ void put_literal16(BitStager16& bs, uint32_t s_lit_sa
     else { const uint32_t c2 = lds_u32(s_lit_saddr + lit_off16<2>(px, 0u)); bs.put(c2 & 0xFFFFu, c2 >> 16); }
 }
 
-// the 4 literal codes of one 32-bit word of filtered bytes, in byte order, as two <= 24-bit puts
+// the 4 literal codes of one 32-bit word of filtered bytes, in byte order, as two <= 24-bit puts (kPlain: nb == 0, the all-literal path)
+template <bool kPlain = false>
 __device__ __forceinline__ void put_word16(BitStager16& bs, uint32_t s_lit_saddr, uint32_t w, uint32_t nb)
 {
 #if FPNGB_PACK_LIT64
     const uint32_t l64 = s_lit_saddr - 4096u, nb8 = nb << 1;
-    const uint2 f0 = lds_u64(l64 + lit_off16x8<0>(w, nb8)), f1 = lds_u64(l64 + lit_off16x8<1>(w, nb8));
-    const uint2 f2 = lds_u64(l64 + lit_off16x8<2>(w, nb8)), f3 = lds_u64(l64 + lit_off16x8<3>(w, nb8));
+    uint2 f0, f1, f2, f3;
+    if (kPlain) {
+        f0 = lds_u64(l64 + lit_off16x8_plain<0>(w)); f1 = lds_u64(l64 + lit_off16x8_plain<1>(w));
+        f2 = lds_u64(l64 + lit_off16x8_plain<2>(w)); f3 = lds_u64(l64 + lit_off16x8_plain<3>(w));
+    } else {
+        f0 = lds_u64(l64 + lit_off16x8<0>(w, nb8)); f1 = lds_u64(l64 + lit_off16x8<1>(w, nb8));
+        f2 = lds_u64(l64 + lit_off16x8<2>(w, nb8)); f3 = lds_u64(l64 + lit_off16x8<3>(w, nb8));
+    }
 #if FPNGB_PACK_MUL
     bs.put_pow(f0.x + f1.x * f0.y, f0.y * f1.y);                         // the table holds (code, 2^size)
     bs.put_pow(f2.x + f3.x * f2.y, f2.y * f3.y);
@@ -524,7 +554,7 @@ __global__ void __launch_bounds__(32 * kPack16Rows) pack_rows16_kernel(PackParam
             if (__all_sync(kFullMask, lit8 == 0xFFu && ev8 == 0u)) {
                 // (1) all 256 pixels are literals, no run pending (noisy rows): the filtered bytes in order, two codes per put
 #pragma unroll
-                for (int j = 0; j < kHalfWords; j++) put_word16(bs, lit_s, hw[j], 0u);
+                for (int j = 0; j < kHalfWords; j++) put_word16<true>(bs, lit_s, hw[j], 0u);
             } else if (__all_sync(kFullMask, lit8 == 0u)) {
                 // (2) no literal at all (inside long runs): only a run reaching M emits a token
                 if (ev8) put_match16(bs, match_s, M);

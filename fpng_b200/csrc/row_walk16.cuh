@@ -57,8 +57,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 
 // The encode kernels are bound by the ALU pipe (LOP3 / SHF / IADD3 / ISETP / SEL; ncu: ~77 % active) while the FMA pipe idles (~17 %).
 // Multipliers the compiler cannot fold keep a few add / shift-add steps on the FMA pipe as IMAD with a constant-bank operand
-// (a literal 2 or -1 would be strength-reduced to LEA / IADD3, ALU-pipe instructions): {2, -1, 2^8, 2^16, 2^24}.
-static __constant__ uint32_t c_fma_k[5] = {2u, 0xFFFFFFFFu, 1u << 8, 1u << 16, 1u << 24};
+// (a literal 2 or -1 would be strength-reduced to LEA / IADD3, ALU-pipe instructions): {2, -1, 2^8, 2^16, 2^24, 8}.
+static __constant__ uint32_t c_fma_k[6] = {2u, 0xFFFFFFFFu, 1u << 8, 1u << 16, 1u << 24, 8u};
 
 // Adler-32 partial sums of one 16-byte chunk at byte offset 16 * I of the lane's bytes: t1 += sum of bytes, t2 += sum of (position inside
 // the lane's bytes) * byte.  The position weights fold the chunk offset (<= 63: a u8), so a step needs ONE 64-bit multiply-add per lane
