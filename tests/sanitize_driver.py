@@ -22,6 +22,15 @@ for rpw in (5, 1):   # both shapes of the pack kernel: 5 scanlines per warp (lar
                     st, px, *_ = fpng_b200.fpng_decode_memory(png, d)
                     bad += st != 0 or not np.array_equal(px, o.decode(png, d)[1])
 _lib.lib().fpngb_debug_rows_per_warp(0)
+# the opt-in staged write pass of the decoder (and the per-thread one after it) on the same files
+_lib.lib().fpngb_debug_decode_staged(1)
+for kind, w, h, c in cases:
+    img = imagegen.make(kind, w, h, c, 5)
+    png = o.encode(img, w, h, c, 0)
+    for d in (3, 4):
+        st, px, *_ = fpng_b200.fpng_decode_memory(png, d)
+        bad += st != 0 or not np.array_equal(px, o.decode(png, d)[1])
+_lib.lib().fpngb_debug_decode_staged(0)
 d = np.random.RandomState(0).randint(0, 256, 70000, dtype=np.uint8)
 bad += fpng_b200.fpng_crc32(d) != o.crc32(d)
 bad += fpng_b200.fpng_adler32(d) != o.adler32(d)
