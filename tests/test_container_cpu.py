@@ -68,3 +68,110 @@ def test_product_static_code_books_match_oracle(oracle):
         esz, ecd, ehb = oracle.static_table(chans)
         assert np.array_equal(sizes, esz) and hb.value == ehb
         assert np.array_equal(codes[:257], ecd[:257])          # literal codes + end of block (the hook reports no length codes)
+
+
+def _chunk(tag: bytes, body: bytes, good_crc: bool = True) -> bytes:
+    import zlib
+    crc = zlib.crc32(tag + body) & 0xFFFFFFFF
+    if not good_crc:
+        crc ^= 0x5A5A5A5A
+    return len(body).to_bytes(4, "big") + tag + body + crc.to_bytes(4, "big")
+
+
+def _split(png: bytes):
+    """signature, [(tag, body, raw chunk bytes)] of a well-formed PNG"""
+    out, at = [], 8
+    while at < len(png):
+        ln = int.from_bytes(png[at:at + 4], "big")
+        out.append((png[at + 4:at + 8], png[at + 8:at + 8 + ln], png[at:at + 12 + ln]))
+        at += 12 + ln
+    return png[:8], out
+
+
+def test_get_info_chunk_surgery_matches_reference(oracle, ref):
+    """Chunk-level edits with VALID CRCs (bit flips almost always die at the first CRC check): inserted ancillary and unknown
+    critical chunks, duplicated / missing / reordered / wrong-version fdEC, two IDATs, short IDAT, missing IEND, IHDR field edits
+    with a recomputed CRC, chunk types outside A-Z/a-z, trailing bytes.  Product walk (host code of libfpng_b200.so) and the
+    oracle's independently written walk must both return the unmodified reference's code (src/fpng.cpp:2930-3077)."""
+    import fpng_b200
+    n = 0
+    seen = set()
+    for png, w, h, c in files(oracle):
+        sig, ch = _split(png)
+        assert [t for t, _, _ in ch] == [b"IHDR", b"fdEC", b"IDAT", b"IEND"]
+        ihdr, fdec, idat, iend = (r for _, _, r in ch)
+        ihdr_body, idat_body = ch[0][1], ch[2][1]
+        anc = _chunk(b"tEXt", b"Comment\0made by a test")
+        cases = {
+            "ancillary before fdEC": sig + ihdr + anc + fdec + idat + iend,
+            "ancillary between fdEC and IDAT": sig + ihdr + fdec + anc + idat + iend,
+            "ancillary after IDAT": sig + ihdr + fdec + idat + anc + iend,
+            "empty ancillary": sig + ihdr + fdec + _chunk(b"zzZz", b"") + idat + iend,
+            "private lower-case first letter, others upper": sig + ihdr + fdec + _chunk(b"aBCD", b"x") + idat + iend,
+            "unknown critical chunk": sig + ihdr + _chunk(b"PLTE", bytes(6)) + fdec + idat + iend,
+            "unknown critical after IDAT": sig + ihdr + fdec + idat + _chunk(b"ABCD", b"") + iend,
+            "ancillary with bad crc": sig + ihdr + fdec + _chunk(b"tEXt", b"abc", good_crc=False) + idat + iend,
+            "IEND with bad crc": sig + ihdr + fdec + idat + _chunk(b"IEND", b"", good_crc=False),
+            "IDAT with bad crc (not checked by get_info)": sig + ihdr + fdec + _chunk(b"IDAT", idat_body, good_crc=False) + iend,
+            "duplicate fdEC": sig + ihdr + fdec + fdec + idat + iend,
+            "no fdEC": sig + ihdr + idat + iend,
+            "fdEC after IDAT": sig + ihdr + idat + fdec + iend,
+            "fdEC wrong version": sig + ihdr + _chunk(b"fdEC", bytes([82, 36, 147, 227, 1])) + idat + iend,
+            "fdEC wrong signature": sig + ihdr + _chunk(b"fdEC", bytes([82, 36, 147, 226, 0])) + idat + iend,
+            "fdEC too short": sig + ihdr + _chunk(b"fdEC", bytes([82, 36, 147, 227])) + idat + iend,
+            "fdEC too long": sig + ihdr + _chunk(b"fdEC", bytes([82, 36, 147, 227, 0, 0])) + idat + iend,
+            "two IDATs": sig + ihdr + fdec + idat + idat + iend,
+            "IDAT split in two": sig + ihdr + fdec + _chunk(b"IDAT", idat_body[:9]) + _chunk(b"IDAT", idat_body[9:]) + iend,
+            "IDAT of 6 bytes": sig + ihdr + fdec + _chunk(b"IDAT", idat_body[:6]) + iend,
+            "IDAT of 7 bytes": sig + ihdr + fdec + _chunk(b"IDAT", idat_body[:7]) + iend,
+            "no IDAT": sig + ihdr + fdec + iend,
+            "no IEND": sig + ihdr + fdec + idat,
+            "no IEND, ancillary last": sig + ihdr + fdec + idat + anc,
+            "IEND first": sig + ihdr + iend + fdec + idat,
+            "IEND with a body": sig + ihdr + fdec + idat + _chunk(b"IEND", b"tail"),
+            "trailing bytes after IEND": png + b"\0" * 19,
+            "chunk type with a digit": sig + ihdr + fdec + _chunk(b"tEX1", b"abc") + idat + iend,
+            "chunk type with '[' (just above Z)": sig + ihdr + fdec + _chunk(b"tEX[", b"abc") + idat + iend,
+            "chunk type with '`' (just below a)": sig + ihdr + fdec + _chunk(b"`EXt", b"abc") + idat + iend,
+            "chunk type with '@' (just below A)": sig + ihdr + fdec + _chunk(b"@EXt", b"abc") + idat + iend,
+            "chunk type with '{' (just above z)": sig + ihdr + fdec + _chunk(b"tEX{", b"abc") + idat + iend,
+            "length field past the end": sig + ihdr + fdec + idat[:4] + b"IDAT",
+            "length 0xFFFFFFFF": sig + ihdr + fdec + b"\xff\xff\xff\xff" + idat[4:] + iend,
+            "second IHDR": sig + ihdr + ihdr + fdec + idat + iend,
+            "IHDR length 14": sig + _chunk(b"IHDR", ihdr_body + b"\0") + fdec + idat + iend,
+            "first chunk not IHDR but 13 bytes": sig + _chunk(b"tEXt", ihdr_body) + fdec + idat + iend,
+        }
+        def with_ihdr(**kw):
+            b = bytearray(ihdr_body)
+            for k, v in kw.items():
+                if k == "w": b[0:4] = v.to_bytes(4, "big")
+                elif k == "h": b[4:8] = v.to_bytes(4, "big")
+                else: b[{"depth": 8, "ctype": 9, "comp": 10, "filt": 11, "lace": 12}[k]] = v
+            return sig + _chunk(b"IHDR", bytes(b)) + fdec + idat + iend
+        cases.update({
+            "w = 0": with_ihdr(w=0), "h = 0": with_ihdr(h=0),
+            "w = 2^24": with_ihdr(w=1 << 24, h=1), "w = 2^24 + 1": with_ihdr(w=(1 << 24) + 1, h=1), "h = 2^24 + 1": with_ihdr(w=1, h=(1 << 24) + 1),
+            "w * h = 2^30": with_ihdr(w=1 << 15, h=1 << 15), "w * h = 2^30 + 2^15": with_ihdr(w=1 << 15, h=(1 << 15) + 1),
+            "w = 0xFFFFFFFF": with_ihdr(w=0xFFFFFFFF),
+            "depth 16": with_ihdr(depth=16), "depth 4": with_ihdr(depth=4),
+            "grey": with_ihdr(ctype=0), "palette": with_ihdr(ctype=3), "grey + alpha": with_ihdr(ctype=4),
+            "RGB <-> RGBA flipped": with_ihdr(ctype=2 if c == 4 else 6),
+            "compression 1": with_ihdr(comp=1), "filter method 1": with_ihdr(filt=1), "interlaced": with_ihdr(lace=1),
+            "bad depth and zero width (dimension check first)": with_ihdr(w=0, depth=1),
+        })
+        for name, bad in cases.items():
+            exp = ref.get_info(bad)
+            got = fpng_b200.fpng_get_info(bad)
+            orc = oracle.get_info(bad)
+            assert got[0] == exp[0], (name, got, exp)
+            assert orc[0] == exp[0], (name, orc, exp)
+            if exp[0] == 0:
+                assert got[1:] == tuple(exp[1:4]) and tuple(orc[1:4]) == tuple(exp[1:4]), (name, got, orc, exp)
+                st, ww, hh, cc, ofs, ln = fpng_b200.get_info_ex(bad)
+                assert bad[ofs + 4:ofs + 8] == b"IDAT" and int.from_bytes(bad[ofs:ofs + 4], "big") == ln, name
+            seen.add(exp[0])
+            n += 1
+    assert n > 350
+    # the edits reach every code the walk can return (src/fpng.h:57-77): success, NOT_FPNG, NOT_PNG, HEADER_CRC32, INVALID_DIMENSIONS,
+    # CHUNK_PARSING, INVALID_IDAT
+    assert seen == {0, 1, 3, 4, 5, 7, 8}, seen
