@@ -68,6 +68,14 @@ def test_product_static_code_books_match_oracle(oracle):
         esz, ecd, ehb = oracle.static_table(chans)
         assert np.array_equal(sizes, esz) and hb.value == ehb
         assert np.array_equal(codes[:257], ecd[:257])          # literal codes + end of block (the hook reports no length codes)
+        # ... and, independently of the oracle, the tables the reference itself stores (tests/golden/static_tables.json, read from
+        # the reference source text by tests/golden/make_static_tables.py: fpng.cpp:532-562 and the RGBA pair below it)
+        import json, os
+        g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "static_tables.json")))[str(chans)]
+        assert list(sizes) == g["sizes"]
+        assert all(codes[i] == g["codes"][i] for i in range(257) if g["sizes"][i])
+        assert hb.value == 8 * len(g["header_bytes"]) + g["bit_buf_size"]
+        assert np.array_equal(esz, g["sizes"]) and all(ecd[i] == g["codes"][i] for i in range(288) if g["sizes"][i])
 
 
 def _chunk(tag: bytes, body: bytes, good_crc: bool = True) -> bytes:
