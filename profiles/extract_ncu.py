@@ -1,7 +1,8 @@
 """Summarises `ncu --set full` reports (gpurun_out/*.ncu-rep) into small tracked files under profiles/:
    <name>_raw.csv (selected raw metrics), <name>_opmix.txt (SASS opcode mix + top stall lines) and traffic.json
    (DRAM bytes per launch of each kernel, used by bench.py for roofline.traffic).
-Usage: python profiles/extract_ncu.py <report.ncu-rep> <name> <kernel-key> <images-in-capture>"""
+Usage: python profiles/extract_ncu.py <report.ncu-rep> <name> <kernel-key> <images-in-capture> [kernel-regex]
+(kernel-regex selects one kernel of a report that holds several: passed to `ncu -i ... -k regex:<kernel-regex>`)"""
 import collections, csv, json, os, subprocess, sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -12,7 +13,8 @@ KEEP = ('gpu__time_duration', 'dram__bytes', 'gpu__dram_throughput', 'sm__throug
 
 def main():
     rep, name, key, images = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    sel = ['-k', 'regex:' + sys.argv[5]] if len(sys.argv) > 5 else []
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     m = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
@@ -20,9 +22,11 @@ def main():
         for h in hdr:
             if h.startswith(KEEP) and 'not_issued' not in h:
                 f.write(f'{h},{u[h]},{m[h]}\n')
-    src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     h2 = rows[1]; si, ii, st = h2.index('Source'), h2.index('Instructions Executed'), h2.index('# Samples')
+    nxt = [i for i, r in enumerate(rows) if i > 1 and r and r[0] == 'Kernel Name']     # a filtered multi-kernel report repeats the block
+    if nxt: rows = rows[:nxt[0]]
     ops, tot = collections.Counter(), 0
     for r in rows[2:]:
         if len(r) <= ii: continue
