@@ -395,7 +395,7 @@ def run_ours(args, wl):
                    "g1_noise": "gradient + uniform integer noise in [-3, 3] from numpy RandomState(1234 + i % 16).randint (MT19937; SURVEY 8d words it as std::mt19937(1234 + i): same engine, different integer mapping, 16 distinct noise fields per batch); both arms use this generator"},
         "clocks": clocks, "gpu_launches": int(launches), "per_rank_ms_per_step": per_rank_ms,
         "scaling_note": None if world == 1 else "weak scaling, no data-path collective: every rank encodes its own 128-image shard; --gpus 1 defaults to C2 "
-                        "(BASELINE config 2), --gpus N>1 to C3 (config 3): compare with `--gpus 1 --workload c3` (profiles/README.md) for the same-workload N=1 value",
+                        "(BASELINE config 2), --gpus N>1 to C3 (config 3): the same-workload N=1 value is the `same_workload_as_multi_gpu` key of the `--gpus 1` line (or `--gpus 1 --workload c3`)",
         "kernels_ms": kern, "roofline": roof(dominant), "roofline_scan": roof("fused" if fused_path else "scan"),
         "encoder": "single-pass fused kernel (encode_fused.cu: filter + match + code emission + bit placement in one read of the pixels)" if fused_path
                    else "two-kernel scan + pack" + (" (IDAT CRC by the file-reading kernel)" if args.encoder == "two_kernel_file_crc" else
@@ -596,6 +596,44 @@ def run_ours(args, wl):
                    "per_rank_gbs": {"h2d": n_e2e * w * h * c * e2e_steps / 1e9 / dt, "d2h": int(hsizes.astype(np.int64).sum()) * e2e_steps / 1e9 / dt},
                    "matches_device_path": bool(e2e_ok)}
 
+    # ---- N = 1 under `--workload auto` (the driver's call): also time the workload the N > 1 runs use (C3, the same per-GPU batch),
+    # so that the N > 1 lines can be read against a same-workload single-GPU number of the same round.  Last GPU leg of the run and
+    # self-contained: a failure here only replaces the key by its error text.
+    if world == 1 and getattr(args, "auto_workload", False) and not args.images and args.encoder == "default":
+        try:
+            wl3 = WORKLOADS["c3"]
+            w3, h3, ch3, fl3, n3 = wl3["w"], wl3["h"], wl3["chans"], wl3["flags"], wl3["images"]
+            b3 = make_device_batch(wl3, args.kind, n3, dev)
+            stride3 = (fpng_b200.max_encoded_size(w3, h3, ch3) + 15) // 16 * 16
+            out3 = torch.empty((n3, stride3), dtype=torch.uint8, device=dev)
+            sizes3 = torch.empty((n3,), dtype=torch.int32, device=dev)
+
+            def step3():
+                fpng_b200.encode_batch_device(b3, fl3, out=out3, sizes=sizes3, stream=stream.cuda_stream)
+
+            for _ in range(3):
+                step3()
+            torch.cuda.synchronize(dev)
+            steps3 = max(1, min(args.steps, 10))
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_a.record(stream)
+            for _ in range(steps3):
+                step3()
+            ev_b.record(stream)
+            torch.cuda.synchronize(dev)
+            ms3 = ev_a.elapsed_time(ev_b) / steps3
+            fsz3 = int(sizes3[0].item()) & 0xFFFFFFFF
+            from oracle.pyoracle import Oracle as _Oracle3
+            par3 = bytes(out3[0, :fsz3].cpu().numpy()) == _Oracle3().encode(workload_image(wl3, args.kind, 0), w3, h3, ch3, fl3)
+            line["same_workload_as_multi_gpu"] = {
+                "workload": wl3["name"], "kind": args.kind, "images": n3, "value": n3 * w3 * h3 / MP / (ms3 / 1e3), "unit": "MP/s",
+                "ms_per_step": ms3, "steps": steps3, "parity_image0_vs_oracle": bool(par3),
+                "what": "device-resident encode of the per-GPU batch that `--gpus N > 1` runs on every rank (weak scaling: N x this value is the "
+                        "ideal N-GPU `value`); the headline `value` of this line is C2, BASELINE config 2"}
+            del b3, out3, sizes3
+        except Exception as e:                                    # noqa: BLE001 -- never let the extra leg cost the line
+            line["same_workload_as_multi_gpu"] = {"error": repr(e)[:300]}
+
     if rank == 0 and world == 1 and not args.no_cpu:
         vals, cores, sample, kind = cpu_reference_run(wl, args.kind, args.cpu_seconds)
         line["cpu_baseline"] = {"value": float(vals[0]), "unit": "MP/s", "cores": cores, "kind": kind, "sample": sample}
@@ -647,6 +685,7 @@ def main():
                     help="default: the library's choice; two_kernel: scan+pack with the chunked CRC overlap; two_kernel_serial: scan+pack, serial; two_kernel_file_crc: scan+pack, IDAT CRC by the file-reading kernel instead of the pack kernel; fused: single-pass encoder")
     ap.add_argument("--own-files", action="store_true", help="decode leg: use the GPU-written files instead of reference-written ones")
     args = ap.parse_args()
+    args.auto_workload = args.workload == "auto"
     if args.workload == "auto":
         args.workload = "c2" if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) <= 1 else "c3"
     wl = WORKLOADS[args.workload]
