@@ -49,6 +49,11 @@ __device__ static void rank_sort(HuffScratch& s, uint32_t n, uint32_t lane)
 
 // Serial part (lane 0): lengths from sorted counts, limited to maxlen; writes s.size[] for `table_len` symbols and
 // canonical bit-reversed codes into s.code[].
+// ATTRIBUTION: the first block is the in-place minimum-redundancy code-length algorithm of Alistair Moffat and Jyrki Katajainen
+// ("In-place calculation of minimum-redundancy codes", 1995; reference implementation by the authors, November 1996), which the
+// reference also uses and credits (fpng.cpp:638-659, via miniz); the second block is the Kraft-sum length limiter of miniz /
+// fpng.cpp:663-674.  Both are restated here on purpose with the SAME order of operations and tie-breaking: 2-pass files are
+// byte-identical to the reference's only if equal counts receive the same lengths.
 __device__ static void lengths_and_codes(HuffScratch& s, int n, int table_len, int maxlen)
 {
     uint16_t* A = s.key;
