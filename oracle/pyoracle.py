@@ -3,6 +3,8 @@
 * ``Oracle``  -> oracle/liboracle.so   (our C restatement, oracle/fpng_oracle.c; always buildable)
 * ``Ref``     -> oracle/_ref/libfpng_ref.so (the unmodified reference + lodepng + stb_image, built from
                  /root/reference/src by oracle/Makefile when that tree exists; travels prebuilt to the GPU box)
+* ``Verifiers`` -> oracle/_ref/libpng_verifiers.so (wuffs + pvpng, the other two independent decoders of the reference's
+                 round-trip check, src/fpng_test.cpp:1403-1445 / 1571-1606; same build rule)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
 The product package (fpng_b200) never does.
@@ -20,6 +22,7 @@ ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libfpng_ref.so")
 REF_TRAIN_SO = os.path.join(HERE, "_ref", "libfpng_ref_train.so")
 REF_PATCH_SO = os.path.join(HERE, "_ref", "libfpng_ref_patch.so")
+VERIFIERS_SO = os.path.join(HERE, "_ref", "libpng_verifiers.so")
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -33,7 +36,8 @@ def build(force: bool = False) -> None:
     ref_stale = ref_possible and (
         (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_shim.cpp"))
         or (not os.path.exists(REF_TRAIN_SO)) or os.path.getmtime(REF_TRAIN_SO) < os.path.getmtime(os.path.join(HERE, "ref_train_shim.cpp"))
-        or (not os.path.exists(REF_PATCH_SO)) or os.path.getmtime(REF_PATCH_SO) < os.path.getmtime(os.path.join(HERE, "ref_patch_shim.cpp")))
+        or (not os.path.exists(REF_PATCH_SO)) or os.path.getmtime(REF_PATCH_SO) < os.path.getmtime(os.path.join(HERE, "ref_patch_shim.cpp"))
+        or (not os.path.exists(VERIFIERS_SO)) or os.path.getmtime(VERIFIERS_SO) < os.path.getmtime(os.path.join(HERE, "verifiers_shim.cpp")))
     if force or stale or ref_stale:
         subprocess.check_call(["make", "-s", "-f", os.path.join(HERE, "Makefile"), "all"], cwd=HERE)
 
@@ -231,6 +235,44 @@ class Ref:
         comp = self.L.ref_stb_decode(_ptr(a), a.size, _ptr(out), out.size, C.byref(ww), C.byref(hh), want_chans)
         px = out[: ww.value * hh.value * want_chans].copy() if comp else None
         return comp, px, ww.value, hh.value
+
+
+class Verifiers:
+    """wuffs (checksums verified) and pvpng, compiled unmodified from the reference tree (oracle/verifiers_shim.cpp)."""
+
+    @staticmethod
+    def available() -> bool:
+        try:
+            build()
+        except Exception:
+            pass
+        return os.path.exists(VERIFIERS_SO)
+
+    def __init__(self):
+        if not Verifiers.available():
+            raise RuntimeError("oracle/_ref/libpng_verifiers.so is not built (reference sources absent?)")
+        L = C.CDLL(VERIFIERS_SO)
+        L.ver_wuffs_decode_rgba.restype = C.c_int
+        L.ver_wuffs_decode_rgba.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, u32p, u32p]
+        L.ver_pvpng_decode.restype = C.c_int
+        L.ver_pvpng_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t, u32p, u32p, u32p]
+        self.L = L
+
+    def wuffs_decode_rgba(self, data, w_hint: int, h_hint: int, ignore_checksums: bool = False):
+        """-> (rc, pixels[h*w*4] or None, w, h); rc 0 = decoded AND (unless ignored) IDAT CRC-32 / zlib Adler-32 correct"""
+        a = _as_u8(data)
+        out = np.empty(max(1, w_hint * h_hint * 4), dtype=np.uint8)
+        ww, hh = C.c_uint32(), C.c_uint32()
+        rc = self.L.ver_wuffs_decode_rgba(_ptr(a), a.size, int(ignore_checksums), _ptr(out), out.size, C.byref(ww), C.byref(hh))
+        return rc, (out[: ww.value * hh.value * 4].copy() if rc == 0 else None), ww.value, hh.value
+
+    def pvpng_decode(self, data, desired_chans: int, w_hint: int, h_hint: int):
+        """-> (rc, pixels[h*w*desired] or None, w, h, channels in file)"""
+        a = _as_u8(data)
+        out = np.empty(max(1, w_hint * h_hint * desired_chans), dtype=np.uint8)
+        ww, hh, cc = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        rc = self.L.ver_pvpng_decode(_ptr(a), a.size, desired_chans, _ptr(out), out.size, C.byref(ww), C.byref(hh), C.byref(cc))
+        return rc, (out[: ww.value * hh.value * desired_chans].copy() if rc == 0 else None), ww.value, hh.value, cc.value
 
 
 class RefTrainer:

@@ -30,6 +30,19 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def verifiers():
+    """wuffs (verifies IDAT CRC-32 and zlib Adler-32) and pvpng: the other two independent decoders of the reference's round-trip
+    check (src/fpng_test.cpp:1403-1445, 1571-1606), compiled unmodified from the reference tree (oracle/verifiers_shim.cpp)."""
+    from oracle.pyoracle import Verifiers
+    try:
+        if not Verifiers.available():
+            pytest.skip("oracle/_ref/libpng_verifiers.so not available")
+        return Verifiers()
+    except OSError as e:
+        pytest.skip(f"libpng_verifiers.so not loadable: {e}")
+
+
+@pytest.fixture(scope="session")
 def gpu():
     import fpng_b200
     fpng_b200.fpng_init()

@@ -62,6 +62,21 @@ def test_encode_round_trips_through_independent_decoders(gpu, ref):
             assert png == ref.encode(img, w, h, c, flags)                   # byte-exact with the reference encoder
 
 
+def test_encode_round_trips_through_wuffs_and_pvpng(gpu, verifiers):
+    """The harness's other two verifiers (src/fpng_test.cpp:1403-1445 wuffs, 1571-1606 pvpng) on GPU-written files; wuffs runs with
+    its checksum verification ON (the harness switches it off), so it also checks the device-computed IDAT CRC-32 and Adler-32."""
+    for (kind, w, h, c) in (("g1", 301, 57, 3), ("g1", 300, 57, 4), ("runs", 1024, 9, 4), ("g2", 77, 31, 3), ("g0", 640, 48, 4), ("mut", 333, 21, 3)):
+        img = np.asarray(imagegen.make(kind, w, h, c, 5)).reshape(h, w, c)
+        rgba = img if c == 4 else np.concatenate([img, np.full((h, w, 1), 255, np.uint8)], axis=2)
+        for flags in (0, 1, 2):
+            ok, png = gpu.fpng_encode_image_to_memory(img, w, h, c, flags)
+            assert ok
+            rc, px, ww, hh = verifiers.wuffs_decode_rgba(png, w, h)
+            assert rc == 0 and (ww, hh) == (w, h) and np.array_equal(px, rgba.reshape(-1)), (kind, w, h, c, flags)
+            rc, px, ww, hh, cc = verifiers.pvpng_decode(png, c, w, h)
+            assert rc == 0 and (ww, hh, cc) == (w, h, c) and np.array_equal(px, img.reshape(-1)), (kind, w, h, c, flags)
+
+
 def test_encode_python_zlib_and_crc(gpu):
     import struct
     import zlib

@@ -80,3 +80,31 @@ def test_fuzzgen_E_matches_real_harness(ref):
                 assert len(ref.encode(buf, w, h, c, 0)) == size
     finally:
         s.close()
+
+
+def test_five_decoder_round_trip_of_oracle_and_reference_files(oracle, ref, verifiers):
+    """The reference's integration check (src/fpng_test.cpp:1237-1445, 1571-1606: fpng, lodepng, stb_image, wuffs, pvpng all return
+    the source pixels) on files written by the oracle and by the unmodified reference -- the GPU encoder's files are byte-identical
+    to these (tests/test_encode_gpu.py), and its own five-decoder test runs under `-m gpu`.  wuffs verifies both checksums here."""
+    import imagegen
+    for i, (kind, w, h, c) in enumerate([("g1", 301, 57, 3), ("g1", 300, 57, 4), ("runs", 1024, 9, 4), ("g2", 77, 31, 3), ("g0", 640, 48, 4),
+                                          ("mut", 333, 21, 3), ("zero", 1, 1, 4), ("g1", 1, 9, 3), ("g1", 8194, 2, 3)]):
+        img = np.asarray(imagegen.make(kind, w, h, c, i)).reshape(h, w, c)
+        rgba = img if c == 4 else np.concatenate([img, np.full((h, w, 1), 255, np.uint8)], axis=2)
+        for flags in (0, 1, 2):
+            png = oracle.encode(img, w, h, c, flags)
+            assert png == ref.encode(img, w, h, c, flags)
+            st, px, ww, hh, cc = ref.decode(png, c)
+            assert st == 0 and np.array_equal(px, img.reshape(-1))
+            err, px, ww, hh = ref.lodepng_decode(png, c)
+            assert err == 0 and np.array_equal(px, img.reshape(-1))
+            comp, px, ww, hh = ref.stb_decode(png, c)
+            assert comp == c and np.array_equal(px, img.reshape(-1))
+            rc, px, ww, hh = verifiers.wuffs_decode_rgba(png, w, h)
+            assert rc == 0 and (ww, hh) == (w, h) and np.array_equal(px, rgba.reshape(-1)), (kind, w, h, c, flags)
+            rc, px, ww, hh, cc = verifiers.pvpng_decode(png, c, w, h)
+            assert rc == 0 and (ww, hh, cc) == (w, h, c) and np.array_equal(px, img.reshape(-1)), (kind, w, h, c, flags)
+            # a flipped checksum bit is caught by wuffs (IDAT CRC-32: 16 bytes from the end; Adler-32: the 4 bytes before it)
+            for pos in (len(png) - 13, len(png) - 17):
+                bad = bytearray(png); bad[pos] ^= 0x10
+                assert verifiers.wuffs_decode_rgba(bytes(bad), w, h)[0] == 1
