@@ -183,3 +183,65 @@ def test_get_info_chunk_surgery_matches_reference(oracle, ref):
     # the edits reach every code the walk can return (src/fpng.h:57-77): success, NOT_FPNG, NOT_PNG, HEADER_CRC32, INVALID_DIMENSIONS,
     # CHUNK_PARSING, INVALID_IDAT
     assert seen == {0, 1, 3, 4, 5, 7, 8}, seen
+
+
+def test_get_info_random_chunk_sequences_match_reference(oracle, ref):
+    """Property test: random chunk sequences drawn from a vocabulary of well-formed and damaged chunks (valid and invalid CRCs, bad type
+    characters, fdEC / IDAT / IEND in any number and order, IHDR field variants, random truncation) -- product walk == oracle walk ==
+    unmodified reference (code, and w/h/chans + IDAT location on success).  Deterministic (fixed seed)."""
+    import fpng_b200
+    rs = np.random.RandomState(2024)
+    sig = bytes([137, 80, 78, 71, 13, 10, 26, 10])
+
+    def ihdr():
+        plain = rs.rand() < 0.7                                                 # mostly a valid header, so that the chunk rules are reached
+        w = int(rs.choice([1, 7, 640, 65535, 65536, 1 << 15] if plain else [0, 1 << 24, (1 << 24) + 1, 1 << 15]))
+        h = int(rs.choice([1, 9, 480, 1 << 15] if plain else [0, (1 << 15) + 1, 1 << 24, 3]))
+        depth = 8 if plain else int(rs.choice([8, 16, 1])); ctype = int(rs.choice([2, 6] if plain else [2, 6, 0, 3, 4]))
+        flags = [int(rs.rand() < (0.0 if plain else 0.1)) for _ in range(3)]
+        body = w.to_bytes(4, "big") + h.to_bytes(4, "big") + bytes([depth, ctype] + flags)
+        if rs.rand() < 0.03:
+            body += b"\0"
+        return _chunk(b"IHDR", body, good_crc=rs.rand() > 0.03)
+
+    def piece():
+        k = rs.randint(0, 12)
+        good = rs.rand() > 0.1
+        if k <= 2:
+            return _chunk(b"fdEC", bytes([82, 36, 147, 227, 0]) if rs.rand() > 0.15 else bytes(rs.randint(0, 256, rs.randint(0, 8), dtype=np.uint8)), good)
+        if k <= 5:
+            return _chunk(b"IDAT", bytes(rs.randint(0, 256, int(rs.choice([0, 6, 7, 8, 40, 200])), dtype=np.uint8)), good)
+        if k <= 7:
+            return _chunk(b"IEND", b"" if rs.rand() > 0.1 else b"x", good)
+        if k == 8:
+            return _chunk(bytes(rs.choice([b"tEXt", b"gAMA", b"zTXt", b"aaaa", b"prIv"])), bytes(rs.randint(0, 256, rs.randint(0, 20), dtype=np.uint8)), good)
+        if k == 9:
+            return _chunk(bytes(rs.choice([b"PLTE", b"ABCD", b"IDAU", b"Idat"])), bytes(rs.randint(0, 256, rs.randint(0, 20), dtype=np.uint8)), good)
+        if k == 10:
+            t = bytearray(b"tEXt"); t[rs.randint(0, 4)] = int(rs.choice([48, 64, 91, 96, 123, 0, 255]))
+            return _chunk(bytes(t), b"abc", good)
+        return bytes(rs.randint(0, 256, rs.randint(1, 16), dtype=np.uint8))      # raw garbage between chunks
+
+    seen = {}
+    for trial in range(3000):
+        f = (sig if rs.rand() > 0.03 else sig[:7] + b"\x0b") + ihdr()
+        if rs.rand() < 0.6:                                                     # bias towards the fpng layout so that deep rules are reached
+            f += _chunk(b"fdEC", bytes([82, 36, 147, 227, 0]))
+        for _ in range(rs.randint(1, 5)):
+            f += piece()
+        if rs.rand() < 0.7:
+            f += _chunk(b"IEND", b"")
+        if rs.rand() < 0.15:
+            f = f[: rs.randint(0, len(f) + 1)]
+        if not f:
+            continue
+        exp = ref.get_info(f)
+        got = fpng_b200.fpng_get_info(f)
+        orc = oracle.get_info(f)
+        assert got[0] == exp[0] and orc[0] == exp[0], (trial, got, orc, exp, f[:80])
+        if exp[0] == 0:
+            assert got[1:] == tuple(exp[1:4]) and tuple(orc[1:4]) == tuple(exp[1:4])
+            st, ww, hh, cc, ofs, ln = fpng_b200.get_info_ex(f)
+            assert f[ofs + 4:ofs + 8] == b"IDAT" and int.from_bytes(f[ofs:ofs + 4], "big") == ln
+        seen[exp[0]] = seen.get(exp[0], 0) + 1
+    assert set(seen) == {0, 1, 3, 4, 5, 7, 8} and seen[0] >= 20, seen
