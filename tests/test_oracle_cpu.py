@@ -122,3 +122,42 @@ def test_static_tables_match_reference_source(oracle):
         sizes, codes, hdr_bits = oracle.static_table(chans)
         for i, (s, c) in enumerate(pairs):
             assert sizes[i] == int(s) and (int(s) == 0 or codes[i] == int(c)), (chans, i)
+
+
+def test_oracle_decode_vs_reference_on_stream_mutations(oracle, ref):
+    """The decoder fuzz of the reference (`fpng_test -f` under zzuf, README.md:185-189) as a seeded CPU test: byte overwrites, bit flips,
+    short random splices, byte swaps and block-header damage inside the IDAT payload (its CRC is not checked by the decoder, fpng.cpp
+    F9), 1-pass / 2-pass / stored files, both desired channel counts -- status AND pixels of the oracle must equal the unmodified
+    reference's.  About a quarter of the mutants still decode (to different pixels): the comparison is not just 'both reject'."""
+    import imagegen
+    rs = np.random.RandomState(77)
+    n = ok = 0
+    for kind, w, h, c, fl in [("g1", 97, 31, 4, 0), ("g1", 160, 24, 3, 0), ("g0", 256, 40, 4, 0), ("runs", 300, 17, 3, 0), ("g1", 128, 32, 3, 1),
+                               ("runs", 301, 9, 4, 1), ("g2", 40, 9, 3, 0), ("mut", 120, 33, 4, 0), ("g0", 333, 20, 3, 1), ("g1", 40, 12, 4, 2)]:
+        png = oracle.encode(imagegen.make(kind, w, h, c, 5), w, h, c, fl)
+        idat, end = png.index(b"IDAT") + 4, len(png) - 16
+        for trial in range(250):
+            bad = bytearray(png)
+            m = rs.randint(0, 5)
+            if m == 0:
+                for _ in range(rs.randint(1, 4)):
+                    bad[rs.randint(idat, end)] = rs.randint(0, 256)
+            elif m == 1:
+                bad[rs.randint(idat, end)] ^= 1 << rs.randint(0, 8)
+            elif m == 2:
+                p, L = rs.randint(idat, end - 8), rs.randint(1, 8)
+                bad[p:p + L] = bytes(rs.randint(0, 256, L, dtype=np.uint8))
+            elif m == 3:
+                a, b = rs.randint(idat, end), rs.randint(idat, end)
+                bad[a], bad[b] = bad[b], bad[a]
+            else:
+                bad[rs.randint(idat, min(idat + 70, end))] = rs.randint(0, 256)
+            bad = bytes(bad)
+            for d in (3, 4):
+                a, b = oracle.decode(bad, d), ref.decode(bad, d)
+                assert a[0] == b[0], (kind, w, h, c, fl, trial, m, d, a[0], b[0])
+                if a[0] == 0:
+                    assert np.array_equal(a[1], b[1]), (kind, w, h, c, fl, trial, m, d)
+                    ok += 1
+                n += 1
+    assert n == 5000 and ok > 500
