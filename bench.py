@@ -259,7 +259,8 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "encode_megapixels_per_sec", "value": v, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": wl["name"], "kind": args.kind, "flags": wl["flags"], "where": "host CPU, reference fpng.cpp SSE4.1/PCLMUL build"},
+        "config": {"workload": wl["name"], "kind": args.kind, "images_per_gpu": args.images or wl["images"], "w": wl["w"], "h": wl["h"],
+                   "chans": wl["chans"], "flags": wl["flags"], "where": "host CPU, reference fpng.cpp SSE4.1/PCLMUL build"},
         "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
