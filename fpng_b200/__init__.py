@@ -11,5 +11,5 @@ from .api import (  # noqa: F401
     fpng_init, fpng_cpu_supports_sse41, fpng_crc32, fpng_adler32, fpng_encode_image_to_memory,
     fpng_encode_image_to_file, fpng_get_info, fpng_decode_memory, fpng_decode_file,
     train_accumulate_device, create_dynamic_block_prefix, set_static_table,
-    max_encoded_size, encode_batch_device, decode_batch_device, decode_batch_host, pack_files_for_device, get_info_ex, launch_count,
+    max_encoded_size, encode_batch_device, decode_batch_device, decode_batch_host, decode_files, pack_files_for_device, get_info_ex, launch_count,
 )

@@ -219,6 +219,38 @@ def decode_batch_host(file_ptrs, sizes, desired_channels: int, out, out_stride: 
     return rc, w.value, h.value, c.value, status
 
 
+def decode_files(files, desired_channels: int):
+    """Batch form of fpng_decode_memory (src/fpng.h:108) for a list of files (bytes-like) of ANY mix of dimensions: the C ABI decodes
+    one shape per call (one kernel grid per shape), so the files are container-walked on the host, grouped by (width, height,
+    channels) and every group goes through fpngb_decode_batch_host.  Returns one (status, pixels or None, w, h, chans_in_file) per
+    file, in input order; status is the FPNG_DECODE_* code fpng_decode_memory would return for that file."""
+    if desired_channels not in (3, 4):
+        return [(FPNG_DECODE_INVALID_ARG, None, 0, 0, 0) for _ in files]
+    bufs = [_u8(f) for f in files]
+    results = [None] * len(bufs)
+    groups = {}
+    for i, a in enumerate(bufs):
+        if a.size == 0:
+            results[i] = (FPNG_DECODE_INVALID_ARG, None, 0, 0, 0)
+            continue
+        st, w, h, c, _, _ = get_info_ex(a)
+        if st != FPNG_DECODE_SUCCESS:
+            results[i] = (st, None, w, h, c)
+        elif w * h * desired_channels > 0xFFFFFFFF:
+            results[i] = (FPNG_DECODE_FAILED_DIMENSIONS_TOO_LARGE, None, w, h, c)                 # fpng.cpp:3103-3105
+        else:
+            groups.setdefault((w, h, c), []).append(i)
+    for (w, h, c), idx in groups.items():
+        need = w * h * desired_channels
+        out = np.empty((len(idx), need), dtype=np.uint8)
+        rc, ww, hh, cc, status = decode_batch_host([bufs[i].ctypes.data for i in idx], [bufs[i].size for i in idx], desired_channels, out, need)
+        check(rc, "decode_files")
+        for k, i in enumerate(idx):
+            ok = int(status[k]) == FPNG_DECODE_SUCCESS
+            results[i] = (int(status[k]), out[k].copy() if ok else None, w, h, c)
+    return results
+
+
 # ---- static-table training (reference: FPNG_TRAIN_HUFFMAN_TABLES / fpng_test -t; src/fpng.h:114-120) ----
 def train_accumulate_device(images, counts=None, stream=None):
     """Adds the 16-bit scaled symbol counts of every image of a CUDA uint8 batch [n, h, w, chans] to counts[288] (uint64)."""
