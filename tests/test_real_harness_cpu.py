@@ -91,3 +91,31 @@ def test_training_driver_prints_what_the_real_harness_prints(tmp_path, oracle, h
     assert mine == real_lines[start:], "\n".join(f"{a!r}\n{b!r}" for a, b in zip(mine, real_lines[start:]) if a != b)
     assert "Total alpha files: 3" in mine and "Total opaque files: 4" in mine and "Total failed loading: 1" in mine
     assert tables[3] is not None and tables[4] is not None and len(tables[3][0]) > 40
+
+
+@pytest.mark.parametrize("opts,flags", [((), 0), (("-s",), 1), (("-u",), 2)])
+def test_config1_through_the_real_harness_plumbing(tmp_path, oracle, harness, opts, flags):
+    """BASELINE config 1 ("single 512x512 RGBA synthetic gradient, 1-pass encode ... (fpng_test plumbing)") through the REAL harness:
+    the G0 image (alpha = green ramp, so fpng_test's alpha auto-detect keeps it 32bpp, src/fpng_test.cpp:1156-1166) is written as a
+    general PNG, `fpng_test [-s|-u]` loads it with lodepng, encodes, verifies with its five decoders and writes fpng.png
+    (src/fpng_test.cpp:1216) -- which must be byte for byte what the oracle (and therefore the GPU encoder, tests/test_encode_gpu.py)
+    produces for the same pixels and flags.  The harness binary is the training-mode build used above (same encoder output)."""
+    from PIL import Image
+    import bench
+    wl = bench.WORKLOADS["c1"]
+    w, h, c = wl["w"], wl["h"], wl["chans"]
+    img = bench.workload_image(wl, "g0", 0)
+    assert img.shape == (h, w, c) and (img[:, :, 3] < 255).any()
+    src = tmp_path / "c1_g0.png"
+    Image.fromarray(img, "RGBA").save(src)
+    r = subprocess.run([harness, *opts, str(src)], capture_output=True, text=True, cwd=tmp_path)        # fpng.png is written without -c
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    assert "Has Alpha: 1" in r.stdout
+    out = (tmp_path / "fpng.png").read_bytes()
+    assert out == oracle.encode(img, w, h, c, flags)
+    r = subprocess.run([harness, "-c", *opts, str(src)], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    # CSV row: file, w, h, chans, then {enc s, MB, dec s, enc MP/s, dec MP/s} for qoi, fpng, lodepng, stbi, and pvpng's two
+    row = [t.strip() for t in r.stdout.strip().splitlines()[-1].split(",")]
+    assert row[1:4] == ["512", "512", "4"] and len(row) == 4 + 4 * 5 + 2
+    assert abs(float(row[10]) - len(out) / (1024.0 * 1024.0)) < 1e-5 and float(row[12]) > 0 and float(row[13]) > 0
