@@ -1,9 +1,13 @@
-"""tools/train_tables.py (the `fpng_test -t` counterpart) against the REAL harness: the unmodified reference's fpng_test is compiled
+"""Tests against the REAL reference harness (fpng_test compiled from /root/reference/src where it lies, test-only, into oracle/_ref/).
+
+1. tools/train_tables.py (the `fpng_test -t` counterpart) against the REAL harness: the unmodified reference's fpng_test is compiled
 with its own FPNG_TRAIN_HUFFMAN_TABLES=1 switch (into oracle/_ref/, test-only) and run on a listing of PNG files; the driver -- with
 the reference trainer (oracle/_ref/libfpng_ref_train.so) standing in for the GPU backend, since this test has no device -- must print
 the same text: per-file lines (dimensions, alpha detection src/fpng_test.cpp:808-821), totals, and both C tables character for
 character (src/fpng_test.cpp:893-961).  The GPU backend's two calls (histogram accumulation, prefix builder) are pinned to the same
-reference trainer by tests/test_training_gpu.py."""
+reference trainer by tests/test_training_gpu.py.
+
+2. BASELINE config 1 through the harness's own plumbing (see test_config1_through_the_real_harness_plumbing)."""
 import io
 import os
 import subprocess
