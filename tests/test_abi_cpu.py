@@ -62,3 +62,22 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("// host twin", ""), f"{f} references oracle/"
+
+
+def test_cxx_callers_compile_and_link_without_a_gpu(tmp_path):
+    """The C++ programs that sit on the drop-in surface -- tests/cpp/dropin_test.cpp (a caller of include/fpng.h) and the
+    fpng_test-equivalent harness tools/fpng_b200_test.cpp -- compile and link against libfpng_b200.so here; without a device they must
+    refuse to run the codec (no CPU fallback): the harness exits non-zero."""
+    import subprocess
+    from fpng_b200 import _build
+    lib = _build.build()
+    exe = str(tmp_path / "dropin_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", os.path.join(ROOT, "tests", "cpp", "dropin_test.cpp"), "-I" + os.path.join(ROOT, "include"),
+                           "-L" + os.path.dirname(lib), "-lfpng_b200", "-Wl,-rpath," + os.path.dirname(lib), "-o", exe])
+    subprocess.check_call(["make", "-s", "-f", os.path.join(ROOT, "tools", "Makefile")])
+    tool = os.path.join(ROOT, "tools", "fpng_b200_test")
+    assert os.path.exists(tool)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([tool, os.path.join(ROOT, "tests", "golden", "example.png")], capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0, r.stdout[-300:]
