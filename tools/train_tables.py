@@ -35,7 +35,12 @@ def load_listing(arg: str):
     if not arg.startswith("@"):
         raise SystemExit("Must specify list of files to read using @filelist.txt")
     names = []
-    with open(arg[1:], "r") as f:
+    try:
+        f = open(arg[1:], "r")
+    except OSError:
+        print(f'Failed opening listing file: "{arg[1:]}"', file=sys.stderr)          # fpng_test.cpp:282-290
+        raise SystemExit(1)
+    with f:
         for line in f:
             line = line.rstrip(" \n\r")
             if line:
